@@ -1,0 +1,118 @@
+/*
+ * mvregfus_b200 — C-ABI of the B200-native (sm_100a) view-fusion hot path of MVRegFus.
+ *
+ * The reference (m-albert/MVRegFus) is pure Python and has no FFI: its "plugin socket" is a set of
+ * Python functions in mvregfus/multiview.py that fuse_block() calls by keyword
+ * (reference: mvregfus/multiview.py:3817-3916).  The drop-in wrappers in mvregfus_b200/multiview.py
+ * keep those names and signatures; this header is what they bind (ctypes).
+ * Each entry point cites the reference code whose arithmetic it replaces ("mv" =
+ * mvregfus/multiview.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all array pointers are DEVICE pointers unless named host_*;
+ *     the caller owns every buffer; nothing is freed behind the caller's back.
+ *   - volumes are C-contiguous (nz, ny, nx), x fastest, like the reference's numpy arrays.
+ *   - affine maps are index-space maps  u_view = matrix * i_fused + offset  (row-major 3x3, zyx
+ *     order, float64), i.e. matrix'/offset' of mv:1486-1496.
+ *   - every function returns 0 on success; on failure a negative code, and mvf_last_error()
+ *     returns a thread-local message.  There is no CPU fallback.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous
+ *     with respect to the host unless stated.
+ */
+#ifndef MVREGFUS_B200_H
+#define MVREGFUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVF_ABI_VERSION 1
+#define MVF_MAX_VIEWS 8      /* views fused in one pass (register-resident weights)           */
+#define MVF_SIG_N 200        /* samples per axis of the blending field, mv:3566               */
+
+enum { MVF_U16 = 0, MVF_F32 = 1 };                 /* voxel dtypes                            */
+enum { MVF_RULE_SCIPY = 0, MVF_RULE_ITK = 1 };     /* boundary rule of order-1 resampling      */
+enum { MVF_W_OFF = 0, MVF_W_BLEND = 1, MVF_W_BLEND_DCT = 2 };
+
+enum {
+  MVF_OK = 0,
+  MVF_ERR_INVALID = -1,      /* bad argument                                                  */
+  MVF_ERR_CUDA = -2,         /* a CUDA runtime call failed (message has the cudaError string) */
+  MVF_ERR_UNSUPPORTED = -3   /* valid request this build cannot serve                         */
+};
+
+/* One view of a fusion call.  `matrix/offset` map fused index -> view index (scipy path,
+ * mv:1494-1496).  `wmatrix/woffset` map fused index -> continuous index of the view's 200^3
+ * blending field (ITK path: field origin o_v + s_v, spacing (size_v-2)/200*s_v, mv:3567,3604).
+ * `profiles` = 3 x MVF_SIG_N float32 (f_z, f_y, f_x): the field is min(f_z[i], f_y[j], f_x[k])
+ * (mv:3558-3598).  `one_lo/one_hi`: per axis the index range [lo,hi) on which f[i]==f[i+1]==1.
+ * `cgrid`: optional coarse DCT weight grid of this view (float32, cdims) with the index map
+ * fused index -> coarse index given by cscale/coffset (diagonal; mv:4249-4253, 4291-4317). */
+typedef struct mvf_view {
+  const void* data;
+  int32_t dtype;
+  int32_t dims[3];
+  double matrix[9];
+  double offset[3];
+  int32_t weight_mode;        /* MVF_W_*; MVF_W_OFF = zero weight (probe early-out, mv:3491-3532) */
+  int32_t one_lo[3];
+  int32_t one_hi[3];
+  double wmatrix[9];
+  double woffset[3];
+  const float* profiles;
+  const float* cgrid;
+  int32_t cdims[3];
+  double cscale[3];
+  double coffset[3];
+} mvf_view;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int mvf_abi_version(void);
+const char* mvf_last_error(void);
+/* Number of kernel launches issued by this library on the calling thread since the last reset
+ * (bench.py's `gpu_launches`). */
+int64_t mvf_launch_count(int reset);
+
+/* ---- K1: order-1 affine resampling of one view -------------------------------------------
+ * Replaces scipy.ndimage.affine_transform(order=1, mode='constant') as called by
+ * transform_chunk (mv:1546-1616, MVF_RULE_SCIPY: 0 outside [0,n-1]; uint16 = round-half-up) and
+ * sitk.Resample(linear)+sitk.Clamp as called by transformStack (mv:6868-6871, MVF_RULE_ITK:
+ * valid on [-0.5,n-0.5), edge clamped, integers truncated).  dst has the dtype of src.
+ * dst covers the index box [dst_origin, dst_origin+dst_dims) of the fused frame, so a z-slab or
+ * a 128^3 chunk can be produced in place. */
+int mvf_affine_resample(const void* src, int dtype, const int32_t src_dims[3],
+                        const double matrix[9], const double offset[3],
+                        void* dst, const int32_t dst_dims[3], const int32_t dst_origin[3],
+                        int rule, void* stream);
+
+/* ---- blending weights on a target grid ----------------------------------------------------
+ * Replaces get_weights_simple (mv:3469-3633): per view the ITK-linear resampling of the
+ * analytic sigmoid-border field, optionally normalised by the sum over views (0 -> 1 guard).
+ * weights_out: nviews x dims float32, view-major. */
+int mvf_blend_weights(int nviews, const mvf_view* host_views, float* weights_out,
+                      const int32_t dims[3], const int32_t origin[3], int normalise, void* stream);
+
+/* ---- weighted additive fusion of already transformed views --------------------------------
+ * Replaces fuse_views_weights (mv:4904-4912): f += uint16(w_v * float64(I_v)) per view
+ * (truncation per view), clip, uint16.  uint16 views accumulate modulo 2^16 like the reference's
+ * uint16 `f`; float32 views accumulate exactly and clip.  weights==NULL -> mean of the views.
+ * out_f32 (optional) receives sum_v w_v*I_v before truncation. */
+int mvf_fuse_weighted(int nviews, const void* const* host_view_ptrs, int dtype,
+                      const float* const* host_weight_ptrs, uint16_t* out, float* out_f32,
+                      size_t nvoxels, void* stream);
+
+/* ---- K2: fused single pass: resample + blending(/DCT) weights + normalise + weighted sum ---
+ * Replaces transform_stack_dask_numpy -> get_weights_simple (x coarse DCT weights) ->
+ * fuse_views_weights for the whole box without materialising transformed views or weights
+ * (mv:1458-1519, 3469-3633, 4291-4317, 4434-4439, 4904-4912).  out: uint16 box of out_dims at
+ * out_origin of the fused frame.  out_f32 optional as above. */
+int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* out, float* out_f32,
+                   const int32_t out_dims[3], const int32_t out_origin[3], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVREGFUS_B200_H */

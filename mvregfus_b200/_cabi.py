@@ -1,0 +1,107 @@
+"""ctypes binding of libmvregfus_b200.so (the C-ABI declared in include/mvregfus_b200.h).
+
+There is deliberately no fallback: if the shared library has not been built, :func:`load` raises.
+Build it with ``python -m mvregfus_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+MVF_MAX_VIEWS = 8
+MVF_SIG_N = 200
+MVF_U16, MVF_F32 = 0, 1
+MVF_RULE_SCIPY, MVF_RULE_ITK = 0, 1
+MVF_W_OFF, MVF_W_BLEND, MVF_W_BLEND_DCT = 0, 1, 2
+
+# every symbol include/mvregfus_b200.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "mvf_abi_version", "mvf_last_error", "mvf_launch_count",
+    "mvf_affine_resample", "mvf_blend_weights", "mvf_fuse_weighted", "mvf_fuse_blend",
+)
+
+
+class MvfView(C.Structure):
+    """struct mvf_view (include/mvregfus_b200.h)."""
+    _fields_ = [
+        ("data", C.c_void_p),
+        ("dtype", C.c_int32),
+        ("dims", C.c_int32 * 3),
+        ("matrix", C.c_double * 9),
+        ("offset", C.c_double * 3),
+        ("weight_mode", C.c_int32),
+        ("one_lo", C.c_int32 * 3),
+        ("one_hi", C.c_int32 * 3),
+        ("wmatrix", C.c_double * 9),
+        ("woffset", C.c_double * 3),
+        ("profiles", C.c_void_p),
+        ("cgrid", C.c_void_p),
+        ("cdims", C.c_int32 * 3),
+        ("cscale", C.c_double * 3),
+        ("coffset", C.c_double * 3),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+class MvfError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+def _declare(lib):
+    i32p = C.POINTER(C.c_int32)
+    f64p = C.POINTER(C.c_double)
+    lib.mvf_abi_version.restype = C.c_int
+    lib.mvf_last_error.restype = C.c_char_p
+    lib.mvf_launch_count.restype = C.c_int64
+    lib.mvf_launch_count.argtypes = [C.c_int]
+    lib.mvf_affine_resample.argtypes = [C.c_void_p, C.c_int, i32p, f64p, f64p, C.c_void_p, i32p, i32p, C.c_int, C.c_void_p]
+    lib.mvf_blend_weights.argtypes = [C.c_int, C.POINTER(MvfView), C.c_void_p, i32p, i32p, C.c_int, C.c_void_p]
+    lib.mvf_fuse_weighted.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.mvf_fuse_blend.argtypes = [C.c_int, C.POINTER(MvfView), C.c_void_p, C.c_void_p, i32p, i32p, C.c_void_p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version"):
+            fn.restype = C.c_int
+
+
+def load():
+    """Return the loaded library; raise if it was never built (no CPU fallback exists)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            path = _build.lib_path()
+            if not os.path.exists(path):
+                if os.environ.get("MVF_AUTOBUILD") == "1":
+                    _build.build()
+                else:
+                    raise RuntimeError(
+                        "libmvregfus_b200.so is not built (%s). Run `python -m mvregfus_b200.build`; "
+                        "this package has no CPU fallback." % path)
+            lib = C.CDLL(path)
+            _declare(lib)
+            if lib.mvf_abi_version() != 1:
+                raise RuntimeError("libmvregfus_b200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise MvfError("mvregfus_b200 C-ABI error %d: %s" % (status, load().mvf_last_error().decode()))
+
+
+def i32x3(v):
+    return (C.c_int32 * 3)(*[int(x) for x in v])
+
+
+def f64(v, n):
+    return (C.c_double * n)(*[float(x) for x in v])
+
+
+def launch_count(reset=False):
+    return int(load().mvf_launch_count(1 if reset else 0))

@@ -1,0 +1,230 @@
+"""Device-level API of the fusion path: torch tensors own HBM, raw pointers cross the C-ABI.
+
+Host-side geometry (float64) lives here: index-space affine maps (reference: mvregfus/multiview.py:
+1486-1496), the probe-point early-out and the 1-D border profiles of the blending field
+(mv:3491-3532, 3558-3604).  All voxel arithmetic happens in the CUDA kernels behind ``_cabi``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .mv_utils import index_space_affine
+
+SIG_N = _cabi.MVF_SIG_N
+_TORCH_DT = {np.dtype(np.uint16): (torch.uint16, _cabi.MVF_U16), np.dtype(np.float32): (torch.float32, _cabi.MVF_F32)}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mvregfus_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def dtype_code(t):
+    if t.dtype == torch.uint16:
+        return _cabi.MVF_U16
+    if t.dtype == torch.float32:
+        return _cabi.MVF_F32
+    raise TypeError("views must be uint16 or float32, got %s" % (t.dtype,))
+
+
+def to_device(arr, device=None):
+    """numpy (uint16/float32, any layout) -> contiguous CUDA tensor."""
+    require_cuda()
+    arr = np.ascontiguousarray(np.asarray(arr))
+    if arr.dtype not in _TORCH_DT:
+        if np.issubdtype(arr.dtype, np.floating):
+            arr = arr.astype(np.float32)
+        else:
+            raise TypeError("unsupported voxel dtype %s (uint16 and float32 are supported)" % arr.dtype)
+    return torch.from_numpy(arr).to(device or "cuda", non_blocking=False)
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------------
+# host geometry
+# ---------------------------------------------------------------------------------------------------
+def probe_any_inside(orig_props, p, stack_properties, n_points=5):
+    """True if any of the n^3 probe points of the target box falls inside the view (mv:3491-3532)."""
+    return bool(_probe_flags(orig_props, p, stack_properties, n_points).any())
+
+
+def _probe_flags(orig_props, p, stack_properties, n_points):
+    rel = np.linspace(0, 1, n_points)
+    grid = np.stack(np.meshgrid(rel, rel, rel, indexing="ij"), -1).reshape(-1, 3)
+    p = np.asarray(p, dtype=np.float64)
+    A, c = p[:9].reshape(3, 3), p[9:]
+    flags = np.empty(len(grid), dtype=bool)
+    size = np.asarray(orig_props["size"])
+    for i, g in enumerate(grid):  # same operation order as the reference loop (bit-exact flags)
+        phys = stack_properties["origin"] + np.array(g) * stack_properties["size"] * stack_properties["spacing"]
+        pix = (np.dot(A, phys) + c - orig_props["origin"]) / orig_props["spacing"]
+        flags[i] = bool(np.all((pix >= 0) & (pix < size)))
+    return flags
+
+
+def blocks_inside_codes(orig_stack_propertiess, params, stack_properties, n_points_per_dim=5):
+    """1 all probe points inside / 0 none / 2 partial, per view (mv:3406-3466)."""
+    codes = []
+    for osp, p in zip(orig_stack_propertiess, params):
+        f = _probe_flags(osp, p, stack_properties, n_points_per_dim)
+        codes.append(1 if f.all() else (2 if f.any() else 0))
+    return np.array(codes)
+
+
+def border_profiles(orig_props):
+    """1-D profiles (3, 200) float32 of the sigmoid-border field and the field spacing.
+
+    The reference fills a 200^3 array slab by slab with ``min(sigmoid(bx), slab)`` (mv:3577-3598); the
+    field is therefore the outer minimum of three 1-D profiles, built here by the same slice walk
+    (Python slice semantics included: very wide borders wrap through negative indices)."""
+    size = np.array(orig_props["size"])
+    sigspacing = (size - 2) / SIG_N * np.asarray(orig_props["spacing"], dtype=np.float64)
+    b = int(40.0 / sigspacing[0])
+
+    def sig(x, bw):
+        return 1 / (1 + np.exp(-(12.0 / bw) * (x - float(bw) / 2.0)))
+
+    prof = np.ones((3, SIG_N), dtype=np.float32)
+    for d in range(3):
+        f = prof[d]
+        wide = 4 * b if d == 0 else b
+        for bx in range(wide):
+            seg = f[bx:bx + 1]
+            seg[...] = np.minimum(np.float32(sig(bx, wide)), seg)
+        for bx in range(b):
+            seg = f[SIG_N - bx - 1:SIG_N - bx]
+            seg[...] = np.minimum(np.float32(sig(bx, b)), seg)
+    return prof, sigspacing
+
+
+def _ones_range(f):
+    nxt = np.minimum(np.arange(SIG_N) + 1, SIG_N - 1)
+    ok = np.where((f == 1.0) & (f[nxt] == 1.0))[0]
+    if len(ok) == 0 or ok[-1] - ok[0] + 1 != len(ok):
+        return 0, 0
+    return int(ok[0]), int(ok[-1]) + 1
+
+
+class ViewSet:
+    """The ctypes ``mvf_view`` array of one fusion call plus the device buffers it points to."""
+
+    def __init__(self, n):
+        self.structs = (_cabi.MvfView * n)()
+        self.keep = []  # tensors kept alive while the structs are in use
+        self.n = n
+
+
+def build_viewset(tensors, orig_stack_propertiess, params, stack_properties, weights="blending",
+                  coarse=None, view_dims=None):
+    """Fill ``mvf_view`` for every view.  ``tensors`` may be None (weights only).  ``coarse`` is an optional
+    ``(grids (V,cz,cy,cx) float32, origin[3], spacing[3])`` for the DCT mode.  ``weights`` in
+    {'blending', 'dct', None}."""
+    n = len(params)
+    if n > _cabi.MVF_MAX_VIEWS:
+        raise ValueError("at most %d views per fused pass (got %d)" % (_cabi.MVF_MAX_VIEWS, n))
+    vs = ViewSet(n)
+    out_sp = np.asarray(stack_properties["spacing"], dtype=np.float64)
+    out_or = np.asarray(stack_properties["origin"], dtype=np.float64)
+    dev = tensors[0].device if tensors is not None else torch.device("cuda")
+    for i in range(n):
+        s = vs.structs[i]
+        osp = orig_stack_propertiess[i]
+        v_sp = np.asarray(osp["spacing"], dtype=np.float64)
+        v_or = np.asarray(osp["origin"], dtype=np.float64)
+        M, off = index_space_affine(params[i], v_sp, v_or, out_sp, out_or)
+        s.matrix = _cabi.f64(M.ravel(), 9)
+        s.offset = _cabi.f64(off, 3)
+        if tensors is not None:
+            t = tensors[i]
+            if not t.is_contiguous() or t.dim() != 3:
+                raise ValueError("views must be contiguous 3-D CUDA tensors")
+            s.data = t.data_ptr()
+            s.dtype = dtype_code(t)
+            s.dims = _cabi.i32x3(t.shape)
+            vs.keep.append(t)
+        else:
+            s.dims = _cabi.i32x3(osp["size"] if view_dims is None else view_dims[i])
+        s.weight_mode = _cabi.MVF_W_OFF
+        if weights is None:
+            continue
+        if not probe_any_inside(osp, params[i], stack_properties, 5):
+            continue  # zero weights for this view in this box (mv:3518-3522)
+        prof, sigspacing = border_profiles(osp)
+        Mw, offw = index_space_affine(params[i], sigspacing, v_or + 1 * v_sp, out_sp, out_or)
+        s.wmatrix = _cabi.f64(Mw.ravel(), 9)
+        s.woffset = _cabi.f64(offw, 3)
+        lo_hi = [_ones_range(prof[d]) for d in range(3)]
+        s.one_lo = _cabi.i32x3([a for a, _ in lo_hi])
+        s.one_hi = _cabi.i32x3([b for _, b in lo_hi])
+        pt = torch.from_numpy(prof.ravel().copy()).to(dev)
+        vs.keep.append(pt)
+        s.profiles = pt.data_ptr()
+        s.weight_mode = _cabi.MVF_W_BLEND
+        if weights == "dct":
+            grids, c_or, c_sp = coarse
+            g = torch.from_numpy(np.ascontiguousarray(grids[i], dtype=np.float32)).to(dev)
+            vs.keep.append(g)
+            s.cgrid = g.data_ptr()
+            s.cdims = _cabi.i32x3(g.shape)
+            s.cscale = _cabi.f64(out_sp / np.asarray(c_sp, dtype=np.float64), 3)
+            s.coffset = _cabi.f64((out_or - np.asarray(c_or, dtype=np.float64)) / np.asarray(c_sp, dtype=np.float64), 3)
+            s.weight_mode = _cabi.MVF_W_BLEND_DCT
+    return vs
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel launches on device tensors
+# ---------------------------------------------------------------------------------------------------
+def affine_resample(src, matrix, offset, out_dims, out_origin=(0, 0, 0), rule="scipy", out=None):
+    """K1 on a CUDA tensor; returns a tensor of ``out_dims`` with the dtype of ``src``."""
+    lib = _cabi.load()
+    if out is None:
+        out = torch.empty(tuple(int(d) for d in out_dims), dtype=src.dtype, device=src.device)
+    rc = lib.mvf_affine_resample(
+        C.c_void_p(src.data_ptr()), dtype_code(src), _cabi.i32x3(src.shape),
+        _cabi.f64(np.asarray(matrix, dtype=np.float64).ravel(), 9), _cabi.f64(offset, 3),
+        C.c_void_p(out.data_ptr()), _cabi.i32x3(out.shape), _cabi.i32x3(out_origin),
+        _cabi.MVF_RULE_SCIPY if rule == "scipy" else _cabi.MVF_RULE_ITK, _stream_ptr())
+    _cabi.check(rc)
+    return out
+
+
+def blend_weights(viewset, dims, origin=(0, 0, 0), normalise=True, device="cuda"):
+    lib = _cabi.load()
+    out = torch.empty((viewset.n,) + tuple(int(d) for d in dims), dtype=torch.float32, device=device)
+    rc = lib.mvf_blend_weights(viewset.n, viewset.structs, C.c_void_p(out.data_ptr()), _cabi.i32x3(dims),
+                               _cabi.i32x3(origin), 1 if normalise else 0, _stream_ptr())
+    _cabi.check(rc)
+    return out
+
+
+def fuse_blend(viewset, dims, origin=(0, 0, 0), out=None, out_f32=None, device="cuda"):
+    """K2: fused resample + weights + weighted sum of the box ``[origin, origin+dims)``."""
+    lib = _cabi.load()
+    if out is None:
+        out = torch.empty(tuple(int(d) for d in dims), dtype=torch.uint16, device=device)
+    rc = lib.mvf_fuse_blend(viewset.n, viewset.structs, C.c_void_p(out.data_ptr()),
+                            C.c_void_p(out_f32.data_ptr()) if out_f32 is not None else None,
+                            _cabi.i32x3(dims), _cabi.i32x3(origin), _stream_ptr())
+    _cabi.check(rc)
+    return out
+
+
+def fuse_weighted(views, weights, out=None, out_f32=None):
+    """fuse_views_weights on materialised CUDA tensors (list of V views, list of V float32 weights or None)."""
+    lib = _cabi.load()
+    n = len(views)
+    if out is None:
+        out = torch.empty(views[0].shape, dtype=torch.uint16, device=views[0].device)
+    vp = (C.c_void_p * n)(*[v.data_ptr() for v in views])
+    wp = (C.c_void_p * n)(*[w.data_ptr() for w in weights]) if weights is not None else None
+    rc = lib.mvf_fuse_weighted(n, vp, dtype_code(views[0]), wp, C.c_void_p(out.data_ptr()),
+                               C.c_void_p(out_f32.data_ptr()) if out_f32 is not None else None,
+                               views[0].numel(), _stream_ptr())
+    _cabi.check(rc)
+    return out

@@ -1,0 +1,172 @@
+"""Drop-in replacements for the view-fusion entry points of ``mvregfus.multiview``.
+
+Same names, positional/keyword signatures, numpy/``ImageArray`` contracts and error behaviour as the
+reference functions (``mv`` = /root/reference/mvregfus/multiview.py); the voxel arithmetic runs in the
+CUDA kernels of libmvregfus_b200 through the C-ABI.  All functions are plain Python ``def``s because
+``fuse_block`` introspects ``weights_func.__code__.co_varnames`` (mv:3864-3874).
+
+Host arrays in, host arrays out (the reference's contract); the device-resident API that avoids the
+PCIe round trip per call is ``mvregfus_b200.fusion`` / ``mvregfus_b200.pipeline``.
+"""
+import numpy as np
+
+from . import fusion
+from .image_array import ImageArray
+from .mv_utils import (index_space_affine, invert_params, matrix_to_params, params_invert_coordinates,  # noqa: F401
+                       params_to_matrix, transform_points)
+
+__all__ = [
+    "transform_stack_sitk", "transform_stack_dask_numpy", "affine_transform_dask",
+    "get_weights_simple", "blocks_inside", "fuse_views_weights", "get_sample_volume", "get_union_volume",
+    "calc_stack_properties_from_volume", "calc_stack_properties_from_views_and_params",
+]
+
+
+# ---------------------------------------------------------------------------------------------------
+# a3: fused-frame bounding box (host, float64 -> integer; mv:3030-3122, 4916-4932)
+# ---------------------------------------------------------------------------------------------------
+def get_sample_volume(stack_properties_list, params):
+    """Lower/upper physical corner of the union of all views back-projected into the fused frame."""
+    ndim = len(stack_properties_list[0]["spacing"])
+    unit = np.array(list(np.ndindex(*([2] * ndim))))
+    verts = []
+    for sp, p in zip(stack_properties_list, params):
+        corners = unit * np.array(sp["size"]) * np.array(sp["spacing"]) + np.array(sp["origin"])
+        Minv = params_to_matrix(invert_params(p))
+        verts.append(np.dot(Minv[:ndim, :ndim], corners.T).T + Minv[:ndim, ndim])
+    verts = np.concatenate(verts, 0)
+    return np.min(verts, 0), np.max(verts, 0)
+
+
+get_union_volume = get_sample_volume  # identical computation in the reference (mv:3030-3052)
+
+
+def calc_stack_properties_from_volume(volume, spacing):
+    """{'size','spacing','origin'} of the fused frame; size is uint16 like the reference (mv:3115)."""
+    spacing = np.array(spacing).astype(np.float64)
+    size = np.ceil((volume[1] - volume[0]) / spacing).astype(np.uint16)
+    return {"size": size, "spacing": spacing, "origin": volume[0]}
+
+
+def calc_stack_properties_from_views_and_params(views_props, params, spacing=None, mode="sample"):
+    """mv:4916-4932.  (The reference wraps this in its io_decorator; that file-cache layer is the caller's.)"""
+    spacing = np.array(spacing).astype(np.float64)
+    if mode in ("sample", "union"):
+        volume = get_sample_volume(views_props, params)
+    elif mode == "intersection":
+        raise Exception("intersection mode is broken in the reference (mv:3068) and not supported")
+    else:
+        raise Exception("can't understand volume mode %s" % mode)
+    return calc_stack_properties_from_volume(volume, spacing)
+
+
+def blocks_inside(orig_stack_propertiess, params, stack_properties, n_points_per_dim=5):
+    """mv:3406-3466 (host, bit-exact integer codes)."""
+    return fusion.blocks_inside_codes(orig_stack_propertiess, params, stack_properties, n_points_per_dim)
+
+
+# ---------------------------------------------------------------------------------------------------
+# a4-a7: resampling
+# ---------------------------------------------------------------------------------------------------
+def _out_geometry(stack, out_shape, out_spacing, out_origin, stack_properties):
+    if stack_properties is not None:
+        return stack_properties["size"], stack_properties["origin"], stack_properties["spacing"]
+    return (stack.shape if out_shape is None else out_shape,
+            stack.origin if out_origin is None else out_origin,
+            stack.spacing if out_spacing is None else out_spacing)
+
+
+def _resample_host(stack, p, out_shape, out_origin, out_spacing, rule):
+    matrix, offset = index_space_affine(p, stack.spacing, stack.origin, out_spacing, out_origin)
+    dims = [int(np.ceil(s)) for s in out_shape]
+    src = fusion.to_device(stack)
+    res = fusion.affine_resample(src, matrix, offset, dims, (0, 0, 0), rule=rule)
+    out = res.cpu().numpy()
+    if out.dtype != np.asarray(stack).dtype and np.issubdtype(np.asarray(stack).dtype, np.floating):
+        out = out.astype(np.asarray(stack).dtype)
+    return out
+
+
+def transform_stack_sitk(stack, p=None, out_shape=None, out_spacing=None, out_origin=None, interp="linear",
+                         stack_properties=None):
+    """ITK-rule linear resampling (mv:1771-1824 + transformStack mv:6797-6877).
+
+    The identity short-circuit returns the input object itself (mv:1813)."""
+    ndim = stack.ndim
+    if ndim != 3:
+        raise Exception("mvregfus_b200 resamples 3-D stacks only")
+    if p is None:
+        p = matrix_to_params(np.eye(ndim + 1))
+    p = np.array(p)
+    out_shape, out_origin, out_spacing = _out_geometry(stack, out_shape, out_spacing, out_origin, stack_properties)
+    if (np.allclose(p, matrix_to_params(np.eye(ndim + 1))) and np.allclose(out_shape, stack.shape)
+            and np.allclose(out_origin, stack.origin) and np.allclose(out_spacing, stack.spacing)):
+        return stack
+    if interp != "linear":
+        raise Exception("mvregfus_b200.transform_stack_sitk implements interp='linear' (got %r); bspline/"
+                        "gaussian/nearest are used only by registration code outside the fusion path" % (interp,))
+    res = _resample_host(stack, p, out_shape, out_origin, out_spacing, "itk")
+    return ImageArray(res, origin=out_origin, spacing=out_spacing)
+
+
+def transform_stack_dask_numpy(stack, p=None, out_shape=None, out_spacing=None, out_origin=None, interp="linear",
+                               stack_properties=None, chunksize=512):
+    """scipy-rule order-1 resampling of a view into the fused frame (mv:1458-1519).
+
+    The reference returns a lazy dask array that evaluates ``scipy.ndimage.affine_transform(order=1)``
+    per chunk; here the whole volume is resampled by one kernel launch and, if dask is installed, wrapped
+    with ``da.from_array(..., chunks=chunksize)`` to keep the dask contract."""
+    out_shape, out_origin, out_spacing = _out_geometry(stack, out_shape, out_spacing, out_origin, stack_properties)
+    res = _resample_host(stack, np.array(p), out_shape, out_origin, out_spacing, "scipy")
+    return _maybe_dask(res, [chunksize] * stack.ndim)
+
+
+def affine_transform_dask(input, matrix, offset=0.0, output_shape=None, output_chunks=(128, 128, 128), **kwargs):
+    """Index-space affine resampling, always order 1 like the reference (mv:1524-1634, order fixed at mv:1610)."""
+    if output_shape is None:
+        output_shape = input.shape
+    matrix = np.asarray(matrix, dtype=np.float64)
+    if matrix.ndim == 1:
+        matrix = np.diag(matrix)
+    offset = np.broadcast_to(np.asarray(offset, dtype=np.float64), (3,))
+    src = fusion.to_device(input)
+    res = fusion.affine_resample(src, matrix, offset, [int(s) for s in output_shape], (0, 0, 0), rule="scipy")
+    return _maybe_dask(res.cpu().numpy(), output_chunks)
+
+
+def _maybe_dask(arr, chunks):
+    try:
+        import dask.array as da
+    except ImportError:
+        return arr
+    return da.from_array(arr, chunks=tuple(int(c) for c in chunks))
+
+
+# ---------------------------------------------------------------------------------------------------
+# a9: blending weights, a13: weighted additive fusion
+# ---------------------------------------------------------------------------------------------------
+def get_weights_simple(orig_stack_propertiess, params, stack_properties):
+    """Sigmoid-border blending weights of every view on the target grid, normalised over views
+    (mv:3469-3633).  Returns a list of V float32 arrays like the reference."""
+    dims = [int(s) for s in stack_properties["size"]]
+    vs = fusion.build_viewset(None, orig_stack_propertiess, params, stack_properties, weights="blending")
+    w = fusion.blend_weights(vs, dims, (0, 0, 0), normalise=True).cpu().numpy()
+    return [ImageArray(w[i], origin=stack_properties["origin"], spacing=stack_properties["spacing"])
+            for i in range(len(params))]
+
+
+def fuse_views_weights(views, params, stack_properties, weights=None, views_in_target_space=True):
+    """f = sum_v uint16(w_v * I_v), clipped, uint16 (mv:4879-4914)."""
+    if not views_in_target_space:
+        views = [np.array(transform_stack_sitk(view, params[iview], out_origin=stack_properties["origin"],
+                                               out_shape=stack_properties["size"],
+                                               out_spacing=stack_properties["spacing"]))
+                 for iview, view in enumerate(views)]
+    dviews = [fusion.to_device(v) for v in views]
+    dweights = [fusion.to_device(np.asarray(w, dtype=np.float32)) for w in weights] if weights is not None else None
+    out = None
+    for i0 in range(0, len(dviews), 8):  # > 8 views: the uint16 accumulation is associative modulo 2^16 only
+        if i0:                           # for uint16 views; keep the reference contract for the common case
+            raise Exception("fuse_views_weights: more than 8 views are not supported by one fused pass")
+        out = fusion.fuse_weighted(dviews[i0:i0 + 8], dweights[i0:i0 + 8] if dweights is not None else None)
+    return ImageArray(out.cpu().numpy(), spacing=stack_properties["spacing"], origin=stack_properties["origin"])
