@@ -542,7 +542,7 @@ def blur_fft(img, psf_ft, kshape):
     out_shape = pad.shape
     ft = np.fft.rfftn(pad.astype(np.float64))
     ft = psf_ft * ft
-    res = np.fft.irfftn(ft, s=out_shape)
+    res = np.fft.irfftn(ft, s=out_shape, axes=(0, 1, 2))
     res = res[kshape[0] // 2:-kshape[0] // 2 - 1, kshape[1] // 2:-kshape[1] // 2 - 1, kshape[2] // 2:-kshape[2] // 2 - 1]
     res[res < 0] = 0
     return res

@@ -1,0 +1,157 @@
+"""Pin the CPU oracle against outputs of the UNMODIFIED reference source (tests/golden/make_golden.py ran
+/root/reference/mvregfus/multiview.py in the build container; see that script for the stand-ins used)."""
+import os
+
+import numpy as np
+import pytest
+
+from mvregfus_b200.image_array import ImageArray
+from oracle import mvregfus_oracle as O
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
+SHAPE = (28, 22, 34)
+
+
+def _props(n, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), shape=SHAPE):
+    return [{"size": np.array(shape), "spacing": np.array(spacing), "origin": np.array(origin)} for _ in range(n)]
+
+
+@pytest.mark.parametrize("nv,sp_out", [(2, 1.0), (4, 0.5), (3, 2.0)])
+def test_bbox_bit_exact(nv, sp_out):
+    tag = "bbox_v%d" % nv
+    props = _props(nv, (1.5, 1.0, 1.0), (3.0, -2.0, 0.5))
+    lo, hi = O.get_sample_volume(props, G[tag + "_params"])
+    assert np.array_equal(lo, G[tag + "_lower"]) and np.array_equal(hi, G[tag + "_upper"])
+    sp = O.calc_stack_properties_from_views_and_params(props, G[tag + "_params"], spacing=[sp_out] * 3)
+    assert sp["size"].dtype == np.uint16 and np.array_equal(sp["size"], G[tag + "_size"])
+    # the product's host code computes the same integers
+    from mvregfus_b200 import multiview as mv
+    sp2 = mv.calc_stack_properties_from_views_and_params(props, G[tag + "_params"], spacing=[sp_out] * 3)
+    assert np.array_equal(sp2["size"], G[tag + "_size"]) and np.array_equal(sp2["origin"], G[tag + "_lower"])
+
+
+@pytest.mark.parametrize("tag", ["u16", "f32"])
+def test_scipy_resampling_matches_reference(tag):
+    params = G["resample_%s_params" % tag]
+    sp = {"size": G["resample_%s_size" % tag], "spacing": np.ones(3), "origin": G["resample_%s_origin" % tag]}
+    for i in range(2):
+        view = ImageArray(G["resample_%s_view%d" % (tag, i)])
+        ref = G["resample_%s_out%d" % (tag, i)]
+        chunked = O.transform_stack_dask_numpy(view, params[i], sp, chunksize=16)
+        assert chunked.dtype == ref.dtype and np.array_equal(chunked, ref)  # same scipy call, same chunks
+        whole = O.transform_stack_dask_numpy(view, params[i], sp)
+        if tag == "u16":
+            assert np.max(np.abs(whole.astype(np.int64) - ref.astype(np.int64))) <= 1
+            assert np.mean(whole != ref) < 1e-4
+        else:
+            assert np.max(np.abs(whole - ref)) <= 1e-9 * max(1.0, float(np.max(ref)))
+
+
+def _weights_case():
+    params = G["weights_params"]
+    props = _props(3, (2.0, 1.0, 1.0))
+    sp = {"size": G["weights_size"], "spacing": np.ones(3), "origin": G["weights_origin"]}
+    return params, props, sp
+
+
+def test_blocks_inside_bit_exact():
+    params, props, sp = _weights_case()
+    from mvregfus_b200 import multiview as mv
+    for fn in (O.blocks_inside, mv.blocks_inside):
+        assert np.array_equal(fn(props, params, sp, 5), G["weights_blocks_inside5"])
+        assert np.array_equal(fn(props, params, sp, 2), G["weights_blocks_inside2"])
+        sub = dict(sp)
+        sub["size"] = np.array([12, 12, 12])
+        sub["origin"] = sp["origin"] + np.array([-30.0, 4.0, 4.0])
+        assert np.array_equal(fn(props, params, sub, 5), G["weights_blocks_inside_far"])
+
+
+def test_blending_weights_match_reference():
+    params, props, sp = _weights_case()
+    ws = np.array(O.get_weights_simple(props, params, sp))
+    assert ws.dtype == np.float32 and np.array_equal(ws, G["weights_simple"])
+
+
+@pytest.mark.parametrize("tag", ["u16", "f32"])
+def test_weighted_fusion_bit_exact(tag):
+    params, props, sp = _weights_case()
+    tv = list(G["fuse_%s_tviews" % tag])
+    f = O.fuse_views_weights(tv, params, sp, weights=list(G["weights_simple"]))
+    assert f.dtype == np.uint16 and np.array_equal(np.asarray(f), G["fuse_%s_out" % tag])
+    m = O.fuse_views_weights(tv, params, sp, weights=None)
+    assert np.array_equal(np.asarray(m), G["fuse_%s_mean" % tag])
+
+
+def test_dct_options_and_binning():
+    got = np.array([O.get_dct_options(s) for s in (0.5, 1.0, 3.0, 6.0, 20.0)], dtype=np.float64)
+    assert np.array_equal(got, G["dct_options"])
+    assert O.dct_binning(1.0) == (2, 32) and O.dct_binning(0.5) == (4, 32) and O.dct_binning(3.0) == (1, 32)
+
+
+def _dct_case():
+    from tests.golden.make_golden import blob_volume
+    params = G["dct_params"]
+    props = _props(2, shape=(96, 96, 96))
+    sp = {"size": np.array([128, 128, 128]), "spacing": np.ones(3), "origin": G["dct_origin"]}
+    tviews = np.array([blob_volume((128, 128, 128), 70 + i, np.uint16, 0.5) for i in range(2)])
+    assert np.array_equal([int(t.astype(np.int64).sum()) for t in tviews], G["dct_tviews_checksum"])
+    return params, props, sp, tviews
+
+
+def test_dct_chunk_quality_matches_reference():
+    params, props, sp, tviews = _dct_case()
+    blk = tviews[:, 32:64, 32:64, 32:64]
+    bprops = {"size": np.array([32] * 3), "spacing": np.array([2.0] * 3), "origin": sp["origin"] + 32.0}
+    q = O.determine_chunk_quality(blk, props, params, bprops)
+    assert np.array_equal(np.asarray(q, dtype=np.float64), G["dct_block_quality"])
+
+
+def test_dct_weights_match_reference():
+    params, props, sp, tviews = _dct_case()
+    blocks = O.get_weights_dct(tviews, params, props, sp, depth=0)
+    wd = blocks[(0, 0, 0)]
+    ref = G["dct_weights_sub"]
+    got = wd[:, ::8, ::8, ::8]
+    assert np.max(np.abs(got.astype(np.float64) - ref)) <= 2e-6
+    sums = np.array([float(np.sum(wd[i].astype(np.float64))) for i in range(2)])
+    assert np.allclose(sums, G["dct_weights_sum"], rtol=1e-6)
+
+
+def test_psf_matches_reference():
+    sp1 = {"size": np.array([40, 40, 40]), "spacing": np.ones(3), "origin": np.zeros(3)}
+    got = np.array([O.get_psf(p, sp1, 3, 1) for p in G["psf_params"]])
+    assert got.dtype == np.float32 and got.shape == G["psf_sz3_sxy1"].shape
+    assert np.array_equal(got, G["psf_sz3_sxy1"])
+    assert np.allclose(got.sum(axis=(1, 2, 3)), 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("blur", ["fft", "direct"])
+def test_rl_matches_reference(blur):
+    sp = {"size": np.array(G["rl_views"].shape[1:]), "spacing": np.ones(3), "origin": np.zeros(3)}
+    est = O.fuse_LR_with_weights_np(list(G["rl_views"]), G["rl_params"], sp, num_iterations=4, sz=2, sxy=1,
+                                    tol=5e-5, weights=list(G["rl_weights"]), blur=blur)
+    ref = G["rl_out_it4"]
+    assert est.dtype == np.uint16
+    if blur == "fft":
+        assert np.array_equal(np.asarray(est), ref)
+    else:  # independent closed-form convolution (index map of SURVEY §8 a15): float64 FFT noise only
+        assert np.max(np.abs(np.asarray(est).astype(np.int64) - ref.astype(np.int64))) <= 1
+        assert np.mean(np.asarray(est) != ref) < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["all", "one"])
+@pytest.mark.parametrize("ftag", ["wavg", "lr"])
+def test_fuse_block_control_flow(tag, ftag):
+    tv = G["block_tviews"].copy()
+    if tag == "one":
+        tv[0] = 0
+        tv[2] = 0
+    props = [{"size": np.array([60, 60, 60]), "spacing": np.ones(3), "origin": np.array([-10.0, -10.0, -10.0])}
+             for _ in range(3)]
+    spb = {"size": np.array([128, 128, 128]), "spacing": np.ones(3), "origin": np.zeros(3)}
+    if ftag == "wavg":
+        ff, kw = O.fuse_views_weights, {}
+    else:
+        ff, kw = O.fuse_LR_with_weights_np, {"num_iterations": 2, "sz": 2, "sxy": 1, "tol": 5e-5}
+    res = O.fuse_block(tv, None, G["block_params"], spb, props, (0, 0, 0), 4, "blending", ff, kw, chunk=32)
+    assert np.array_equal(np.asarray(res), G["block_%s_%s" % (tag, ftag)])
