@@ -50,40 +50,52 @@ struct Brick {
   int b0[3];  // view index of brick element (0,0,0); may be negative (zero filled)
   int e[3];   // extents
   int px, pz; // shared-memory pitches (elements)
-  bool skip;  // brick does not intersect the view
+  bool skip;      // brick does not intersect the view
+  bool interior;  // every voxel of the tile maps strictly inside [0, n-1]: no per-voxel boundary test
 };
+
+// Bounding box, in the index space of an affine map, of the voxels of one tile (fp64).
+__device__ __forceinline__ void tile_bbox(const double* m, const double* o, int z0, int y0, int x0, double lo[3], double hi[3]) {
+  const int T[3] = {TZ - 1, TY - 1, TX - 1};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double base = fma(m[d * 3 + 2], (double)x0, fma(m[d * 3 + 1], (double)y0, fma(m[d * 3 + 0], (double)z0, o[d])));
+    double l = base, h = base;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double ext = m[d * 3 + k] * (double)T[k];
+      if (ext < 0) l += ext; else h += ext;
+    }
+    lo[d] = l - 1e-7 * (1.0 + fabs(l));
+    hi[d] = h + 1e-7 * (1.0 + fabs(h));
+  }
+}
 
 __device__ __forceinline__ Brick tile_brick(const KView& kv, int z0, int y0, int x0) {
   Brick b;
-  const int T[3] = {TZ - 1, TY - 1, TX - 1};
-  bool skip = false;
+  double lo[3], hi[3];
+  tile_bbox(kv.m, kv.o, z0, y0, x0, lo, hi);
+  bool skip = false, interior = true;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    double base = fma(kv.m[d * 3 + 2], (double)x0, fma(kv.m[d * 3 + 1], (double)y0, fma(kv.m[d * 3 + 0], (double)z0, kv.o[d])));
-    double lo = base, hi = base;
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      double ext = kv.m[d * 3 + l] * (double)T[l];
-      if (ext < 0) lo += ext; else hi += ext;
-    }
-    lo -= 1e-7 * (1.0 + fabs(lo));
-    hi += 1e-7 * (1.0 + fabs(hi));
-    int i0 = __double2int_rd(lo);
-    int i1 = __double2int_rd(hi) + 1;
+    int i0 = __double2int_rd(lo[d]);
+    int i1 = __double2int_rd(hi[d]) + 1;
     b.b0[d] = i0;
     int e = i1 - i0 + 1;
     b.e[d] = e < kv.be[d] ? e : kv.be[d];
     if (i1 < 0 || i0 > kv.n[d] - 1) skip = true;
+    if (!(lo[d] >= 0.0 && hi[d] <= (double)(kv.n[d] - 1))) interior = false;
   }
   b.px = b.e[2] | 1;
   b.pz = (b.e[1] * b.px) | 1;
   b.skip = skip;
+  b.interior = interior;
   return b;
 }
 
-// Cooperative, coalesced staging of the brick into shared memory; out-of-volume elements are zero.
+// Cooperative, coalesced staging of the brick into shared memory as float32; out-of-volume elements are 0.
 template <typename T>
-__device__ __forceinline__ void stage_brick(const KView& kv, const Brick& bk, T* sm) {
+__device__ __forceinline__ void stage_brick(const KView& kv, const Brick& bk, float* sm) {
   const T* __restrict__ src = reinterpret_cast<const T*>(kv.data);
   const unsigned ex = bk.e[2], ey = bk.e[1];
   const unsigned total = bk.e[0] * ey * ex;
@@ -95,85 +107,124 @@ __device__ __forceinline__ void stage_brick(const KView& kv, const Brick& bk, T*
     unsigned iz = __umulhi(row, my);
     unsigned iy = row - iz * ey;
     int gz = bk.b0[0] + (int)iz, gy = bk.b0[1] + (int)iy, gx = bk.b0[2] + (int)ix;
-    T v = T(0);
+    float v = 0.f;
     if ((unsigned)gz < (unsigned)kv.n[0] && (unsigned)gy < (unsigned)kv.n[1] && (unsigned)gx < (unsigned)kv.n[2])
-      v = __ldg(src + ((size_t)gz * kv.n[1] + gy) * kv.n[2] + gx);
+      v = to_float<T>(__ldg(src + ((size_t)gz * kv.n[1] + gy) * kv.n[2] + gx));
     sm[iz * bk.pz + iy * bk.px + ix] = v;
   }
 }
 
-// Trilinear value at brick-relative coordinate rel (float64), scipy 'constant' rule: 0 when the view
-// coordinate is outside [0, n-1] (ni_interpolation.c NI_GeometricTransform, mode constant).
-template <typename T>
-__device__ __forceinline__ float gather_scipy(const T* sm, const Brick& bk, const KView& kv, const double rel[3]) {
-  int li[3];
-  float t[3], s[3];
-  bool inside = true;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    double lo = -(double)bk.b0[d], hi = (double)(kv.n[d] - 1 - bk.b0[d]);
-    inside = inside && (rel[d] >= lo) && (rel[d] <= hi);
-    int i = __double2int_rd(rel[d]);
-    double fr = rel[d] - (double)i;
-    t[d] = (float)fr;
-    s[d] = (float)(1.0 - fr);
-    i = max(0, min(i, bk.e[d] - 2));
-    li[d] = i;
-  }
-  const T* p = sm + li[0] * bk.pz + li[1] * bk.px + li[2];
-  float c000 = to_float(p[0]), c001 = to_float(p[1]);
-  float c010 = to_float(p[bk.px]), c011 = to_float(p[bk.px + 1]);
-  float c100 = to_float(p[bk.pz]), c101 = to_float(p[bk.pz + 1]);
-  float c110 = to_float(p[bk.pz + bk.px]), c111 = to_float(p[bk.pz + bk.px + 1]);
-  // convex combination with separately rounded t and 1-t: no cancellation for non-negative data
-  float w00 = s[0] * s[1], w01 = s[0] * t[1], w10 = t[0] * s[1], w11 = t[0] * t[1];
-  float r = c000 * (w00 * s[2]);
-  r = fmaf(c001, w00 * t[2], r);
-  r = fmaf(c010, w01 * s[2], r);
-  r = fmaf(c011, w01 * t[2], r);
-  r = fmaf(c100, w10 * s[2], r);
-  r = fmaf(c101, w10 * t[2], r);
-  r = fmaf(c110, w11 * s[2], r);
-  r = fmaf(c111, w11 * t[2], r);
-  return inside ? r : 0.f;
+// Nearest grid point r = rint(u), |u - r| as float32 and the sign of (u - r), from one fp64 coordinate, with
+// two DADDs and one F2F.  Interpolating from the NEAREST corner towards the far one keeps the lerp weight in
+// [0, 0.5], so  near + (far - near) * w  is exact for constant neighbourhoods and relatively accurate for
+// non-negative data (no cancellation against a weight close to 1).
+__device__ __forceinline__ void split_nearest(double u, int& r, float& w, int& neg) {
+  double y = u + MAGIC64;
+  r = __double2loint(y);
+  double d = u - (y - MAGIC64);
+  neg = d < 0.0 ? -1 : 0;  // -1 when the far corner is r-1, 0 when it is r+1 (-0.0 counts as +0)
+  w = fabsf((float)d);
 }
 
-// ITK rule: valid iff -0.5 <= u < n-0.5 per axis, neighbours clamped to the edge, nested lerp
-// a+(b-a)*t x->y->z (itk::LinearInterpolateImageFunction), outside -> 0.
-template <typename T>
-__device__ __forceinline__ float gather_itk(const T* sm, const Brick& bk, const KView& kv, const double rel[3]) {
-  int li[3];
-  float t[3];
+__device__ __forceinline__ float lerp8(const float* p, int ox, int oy, int oz, float wx, float wy, float wz) {
+  float c000 = p[0], c001 = p[ox];
+  float c010 = p[oy], c011 = p[oy + ox];
+  float c100 = p[oz], c101 = p[oz + ox];
+  float c110 = p[oz + oy], c111 = p[oz + oy + ox];
+  float x00 = fmaf(c001 - c000, wx, c000);
+  float x01 = fmaf(c011 - c010, wx, c010);
+  float x10 = fmaf(c101 - c100, wx, c100);
+  float x11 = fmaf(c111 - c110, wx, c110);
+  float y0 = fmaf(x01 - x00, wy, x00);
+  float y1 = fmaf(x11 - x10, wy, x10);
+  return fmaf(y1 - y0, wz, y0);
+}
+
+// Trilinear value at brick-relative coordinate rel (float64), scipy 'constant' rule: 0 when the view
+// coordinate is outside [0, n-1] (ni_interpolation.c NI_GeometricTransform, mode constant).
+template <bool INTERIOR>
+__device__ __forceinline__ float gather_scipy(const float* sm, const Brick& bk, const KView& kv, const double rel[3]) {
+  int r[3], neg[3];
+  float w[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) split_nearest(rel[d], r[d], w[d], neg[d]);
+  const float* p = sm + r[0] * bk.pz + r[1] * bk.px + r[2];
+  const int ox = 1 | neg[2];
+  const int oy = (bk.px ^ neg[1]) - neg[1];
+  const int oz = (bk.pz ^ neg[0]) - neg[0];
+  float val = lerp8(p, ox, oy, oz, w[2], w[1], w[0]);
+  if (!INTERIOR) {
+    bool inside = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      inside = inside && (rel[d] >= -(double)bk.b0[d]) && (rel[d] <= (double)(kv.n[d] - 1 - bk.b0[d]));
+    val = inside ? val : 0.f;
+  }
+  return val;
+}
+
+// ITK rule: valid iff -0.5 <= u < n-0.5 per axis, neighbours clamped to the edge, outside -> 0
+// (itk::LinearInterpolateImageFunction / ResampleImageFilter).
+__device__ __forceinline__ float gather_itk(const float* sm, const Brick& bk, const KView& kv, const double rel[3]) {
+  int off[3], base = 0;
+  float w[3];
   bool inside = true;
+  const int stride[3] = {bk.pz, bk.px, 1};
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     double u = rel[d] + (double)bk.b0[d];
     inside = inside && (u >= -0.5) && (u < (double)kv.n[d] - 0.5);
-    int i = __double2int_rd(u);
-    double fr = u - (double)i;
-    if (i < 0) { i = 0; fr = 0.0; }
-    if (i >= kv.n[d] - 1) { i = kv.n[d] - 1; fr = 0.0; }
-    t[d] = (float)fr;
-    i -= bk.b0[d];
-    li[d] = max(0, min(i, bk.e[d] - 2));
+    int r, neg;
+    split_nearest(u, r, w[d], neg);
+    int near = max(0, min(r, kv.n[d] - 1));
+    int far = max(0, min(r + (1 | neg), kv.n[d] - 1));
+    int ln = max(0, min(near - bk.b0[d], bk.e[d] - 1));
+    int lf = max(0, min(far - bk.b0[d], bk.e[d] - 1));
+    base += ln * stride[d];
+    off[d] = (lf - ln) * stride[d];
   }
-  const T* p = sm + li[0] * bk.pz + li[1] * bk.px + li[2];
-  float c000 = to_float(p[0]), c001 = to_float(p[1]);
-  float c010 = to_float(p[bk.px]), c011 = to_float(p[bk.px + 1]);
-  float c100 = to_float(p[bk.pz]), c101 = to_float(p[bk.pz + 1]);
-  float c110 = to_float(p[bk.pz + bk.px]), c111 = to_float(p[bk.pz + bk.px + 1]);
-  float x00 = fmaf(c001 - c000, t[2], c000);
-  float x01 = fmaf(c011 - c010, t[2], c010);
-  float x10 = fmaf(c101 - c100, t[2], c100);
-  float x11 = fmaf(c111 - c110, t[2], c110);
-  float y0 = fmaf(x01 - x00, t[1], x00);
-  float y1 = fmaf(x11 - x10, t[1], x10);
-  float r = fmaf(y1 - y0, t[0], y0);
-  return inside ? r : 0.f;
+  float val = lerp8(sm + base, off[2], off[1], off[0], w[2], w[1], w[0]);
+  return inside ? val : 0.f;
 }
 
-// ITK-linear sample of the analytic blending field min(f_z[i], f_y[j], f_x[k]) at continuous field index c.
-__device__ __forceinline__ float blend_field(const KView& kv, const double c[3]) {
+// ---- blending field ------------------------------------------------------------------------------
+enum { WT_ZERO = 0, WT_ONE = 1, WT_RAMP = 2, WT_EDGE = 3 };
+
+// Classify a tile against a view's blending field: every voxel outside the field (weight 0), every voxel
+// on the all-ones plateau (weight 1), fully inside the field (fast float32 path) or touching its rim.
+__device__ __forceinline__ int classify_tile(const KView& kv, int z0, int y0, int x0) {
+  if (kv.wmode == MVF_W_OFF) return WT_ZERO;
+  double lo[3], hi[3];
+  tile_bbox(kv.wm, kv.wo, z0, y0, x0, lo, hi);
+  bool zero = false, one = true, ramp = true;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    zero = zero || (hi[d] < -0.5) || (lo[d] >= (double)MVF_SIG_N - 0.5);
+    one = one && (lo[d] >= (double)kv.one_lo[d]) && (hi[d] < (double)kv.one_hi[d]);
+    ramp = ramp && (lo[d] >= 0.0) && (hi[d] < (double)(MVF_SIG_N - 1));
+  }
+  return zero ? WT_ZERO : (one ? WT_ONE : (ramp ? WT_RAMP : WT_EDGE));
+}
+
+__device__ __forceinline__ float field_lerp(const float* f, int i0, int i1, int i2, int j0, int j1, int j2, float t0, float t1, float t2) {
+  float a0 = __ldg(f + i0), a1 = __ldg(f + j0);
+  float b0 = __ldg(f + MVF_SIG_N + i1), b1 = __ldg(f + MVF_SIG_N + j1);
+  float c0 = __ldg(f + 2 * MVF_SIG_N + i2), c1 = __ldg(f + 2 * MVF_SIG_N + j2);
+  float m00 = fminf(a0, b0), m01 = fminf(a0, b1), m10 = fminf(a1, b0), m11 = fminf(a1, b1);
+  float v000 = fminf(m00, c0), v001 = fminf(m00, c1), v010 = fminf(m01, c0), v011 = fminf(m01, c1);
+  float v100 = fminf(m10, c0), v101 = fminf(m10, c1), v110 = fminf(m11, c0), v111 = fminf(m11, c1);
+  float x00 = fmaf(v001 - v000, t2, v000);
+  float x01 = fmaf(v011 - v010, t2, v010);
+  float x10 = fmaf(v101 - v100, t2, v100);
+  float x11 = fmaf(v111 - v110, t2, v110);
+  float y0 = fmaf(x01 - x00, t1, x00);
+  float y1 = fmaf(x11 - x10, t1, x10);
+  return fmaf(y1 - y0, t0, y0);
+}
+
+// ITK-linear sample of the analytic blending field min(f_z[i], f_y[j], f_x[k]) at continuous field index c
+// (exact float64 index arithmetic; used on tiles that touch the rim of the field).
+__device__ __forceinline__ float blend_field_exact(const KView& kv, const double c[3]) {
   int i0[3];
   float t[3];
   bool inside = true, ones = true;
@@ -190,21 +241,8 @@ __device__ __forceinline__ float blend_field(const KView& kv, const double c[3])
   }
   if (!inside) return 0.f;
   if (ones) return 1.f;
-  const float* f = kv.prof;
   int j0 = min(i0[0] + 1, MVF_SIG_N - 1), j1 = min(i0[1] + 1, MVF_SIG_N - 1), j2 = min(i0[2] + 1, MVF_SIG_N - 1);
-  float a0 = __ldg(f + i0[0]), a1 = __ldg(f + j0);
-  float b0 = __ldg(f + MVF_SIG_N + i0[1]), b1 = __ldg(f + MVF_SIG_N + j1);
-  float c0 = __ldg(f + 2 * MVF_SIG_N + i0[2]), c1 = __ldg(f + 2 * MVF_SIG_N + j2);
-  float m00 = fminf(a0, b0), m01 = fminf(a0, b1), m10 = fminf(a1, b0), m11 = fminf(a1, b1);
-  float v000 = fminf(m00, c0), v001 = fminf(m00, c1), v010 = fminf(m01, c0), v011 = fminf(m01, c1);
-  float v100 = fminf(m10, c0), v101 = fminf(m10, c1), v110 = fminf(m11, c0), v111 = fminf(m11, c1);
-  float x00 = fmaf(v001 - v000, t[2], v000);
-  float x01 = fmaf(v011 - v010, t[2], v010);
-  float x10 = fmaf(v101 - v100, t[2], v100);
-  float x11 = fmaf(v111 - v110, t[2], v110);
-  float y0 = fmaf(x01 - x00, t[1], x00);
-  float y1 = fmaf(x11 - x10, t[1], x10);
-  return fmaf(y1 - y0, t[0], y0);
+  return field_lerp(kv.prof, i0[0], i0[1], i0[2], j0, j1, j2, t[0], t[1], t[2]);
 }
 
 // ITK-linear sample of a small float32 grid in global memory (coarse DCT weights, mv:4304-4311).
@@ -247,9 +285,11 @@ __device__ __forceinline__ void affine_base(const double* m, const double* o, in
 
 // Blending (x coarse DCT) weights of the RX voxels of a thread for all V views, normalised exactly like
 // the reference: w_v / sum_v w_v in float32 with a 0 -> 1 guard (mv:3627-3631), and for the DCT mode
-// coarse_v * that, normalised again (mv:4317, 4434-4439).
+// coarse_v * that, normalised again (mv:4317, 4434-4439).  (tz0,ty0,tx0) is the fused-frame index of the
+// tile origin, (gz,gy,gx) of the thread's first voxel.
 template <int V>
-__device__ __forceinline__ void thread_weights(const KView* kvs, int gz, int gy, int gx, float (&w)[V][RX]) {
+__device__ __forceinline__ void thread_weights(const KView* kvs, int tz0, int ty0, int tx0, int gz, int gy, int gx,
+                                               float (&w)[V][RX]) {
   float wsum[RX];
 #pragma unroll
   for (int k = 0; k < RX; ++k) wsum[k] = 0.f;
@@ -257,19 +297,53 @@ __device__ __forceinline__ void thread_weights(const KView* kvs, int gz, int gy,
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const KView& kv = kvs[v];
-    if (kv.wmode == MVF_W_OFF) {
+    const int cls = classify_tile(kv, tz0, ty0, tx0);  // CTA-uniform
+    if (cls == WT_ZERO) {
 #pragma unroll
       for (int k = 0; k < RX; ++k) w[v][k] = 0.f;
       continue;
     }
     dct = dct || (kv.wmode == MVF_W_BLEND_DCT);
+    if (cls == WT_ONE) {
+#pragma unroll
+      for (int k = 0; k < RX; ++k) { w[v][k] = 1.f; wsum[k] += 1.f; }
+      continue;
+    }
     double cb[3];
     affine_base(kv.wm, kv.wo, gz, gy, gx, cb);
+    if (cls == WT_RAMP) {
+      // float32 increments on a float64 base: |error| < 1e-6 field voxels, i.e. < 3e-7 in the weight
+      int ci[3];
+      float cf[3], cm[3];
 #pragma unroll
-    for (int k = 0; k < RX; ++k) {
-      double c[3] = {fma((double)k, kv.wm[2], cb[0]), fma((double)k, kv.wm[5], cb[1]), fma((double)k, kv.wm[8], cb[2])};
-      w[v][k] = blend_field(kv, c);
-      wsum[k] += w[v][k];
+      for (int d = 0; d < 3; ++d) {
+        ci[d] = __double2int_rd(cb[d]);
+        cf[d] = (float)(cb[d] - (double)ci[d]);
+        cm[d] = (float)kv.wm[d * 3 + 2];
+      }
+#pragma unroll
+      for (int k = 0; k < RX; ++k) {
+        int i0[3];
+        float t[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          float c = fmaf((float)k, cm[d], cf[d]);
+          float y = __fadd_rd(c, MAGIC32);
+          t[d] = c - (y - MAGIC32);
+          i0[d] = ci[d] + (__float_as_int(y) - 0x4B400000);
+          i0[d] = max(0, min(i0[d], MVF_SIG_N - 2));  // rounding guard at the bbox limits
+        }
+        float wv = field_lerp(kv.prof, i0[0], i0[1], i0[2], i0[0] + 1, i0[1] + 1, i0[2] + 1, t[0], t[1], t[2]);
+        w[v][k] = wv;
+        wsum[k] += wv;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RX; ++k) {
+        double c[3] = {fma((double)k, kv.wm[2], cb[0]), fma((double)k, kv.wm[5], cb[1]), fma((double)k, kv.wm[8], cb[2])};
+        w[v][k] = blend_field_exact(kv, c);
+        wsum[k] += w[v][k];
+      }
     }
   }
 #pragma unroll
@@ -319,7 +393,7 @@ __device__ __forceinline__ void thread_voxel(int& lz, int& ly, int& lx) {
 template <typename T, int V>
 __global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ FuseArgs<V> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sm = reinterpret_cast<T*>(smem_raw);
+  float* sm = reinterpret_cast<float*>(smem_raw);
   const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
   int lz, ly, lx;
   thread_voxel(lz, ly, lx);
@@ -327,7 +401,7 @@ __global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ 
   const int gz = z + A.org[0], gy = y + A.org[1], gx = x + A.org[2];  // fused-frame index
 
   float w[V][RX];
-  thread_weights<V>(A.v, gz, gy, gx, w);
+  thread_weights<V>(A.v, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], gz, gy, gx, w);
 
   uint32_t acc[RX];
   float accf[RX];
@@ -349,8 +423,8 @@ __global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < RX; ++k) {
       double rel[3] = {fma((double)k, kv.m[2], ub[0]), fma((double)k, kv.m[5], ub[1]), fma((double)k, kv.m[8], ub[2])};
-      float val = gather_scipy<T>(sm, bk, kv, rel);
-      if (sizeof(T) == 2) val = (float)round_half_up_u16(val);  // the transformed view is uint16 (mv:1626)
+      float val = bk.interior ? gather_scipy<true>(sm, bk, kv, rel) : gather_scipy<false>(sm, bk, kv, rel);
+      if (sizeof(T) == 2) val = u16_to_float(round_half_up_u16(val));  // the transformed view is uint16 (mv:1626)
       acc[k] += trunc_product_u16(w[v][k], val);
       accf[k] = fmaf(w[v][k], val, accf[k]);
     }
@@ -358,16 +432,16 @@ __global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ 
 
   if (z >= A.dims[0] || y >= A.dims[1]) return;
   const size_t row = ((size_t)z * A.dims[1] + y) * A.dims[2];
-  uint16_t r[RX];
+  uint32_t r[RX];
 #pragma unroll
-  for (int k = 0; k < RX; ++k) r[k] = sizeof(T) == 2 ? (uint16_t)(acc[k] & 0xFFFFu) : (uint16_t)min(acc[k], 65535u);
+  for (int k = 0; k < RX; ++k) r[k] = sizeof(T) == 2 ? (acc[k] & 0xFFFFu) : min(acc[k], 65535u);
   if (x + RX <= A.dims[2] && (((row + x) & 7) == 0)) {
     uint4 pk;
     pk.x = r[0] | (r[1] << 16); pk.y = r[2] | (r[3] << 16); pk.z = r[4] | (r[5] << 16); pk.w = r[6] | (r[7] << 16);
     *reinterpret_cast<uint4*>(A.out + row + x) = pk;
   } else {
 #pragma unroll
-    for (int k = 0; k < RX; ++k) if (x + k < A.dims[2]) A.out[row + x + k] = r[k];
+    for (int k = 0; k < RX; ++k) if (x + k < A.dims[2]) A.out[row + x + k] = (uint16_t)r[k];
   }
   if (A.outf) {
 #pragma unroll
@@ -381,7 +455,7 @@ __global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ 
 template <typename T, int RULE>
 __global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ ResampleArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sm = reinterpret_cast<T*>(smem_raw);
+  float* sm = reinterpret_cast<float*>(smem_raw);
   const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
   int lz, ly, lx;
   thread_voxel(lz, ly, lx);
@@ -402,7 +476,9 @@ __global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ Re
 #pragma unroll
     for (int k = 0; k < RX; ++k) {
       double rel[3] = {fma((double)k, kv.m[2], ub[0]), fma((double)k, kv.m[5], ub[1]), fma((double)k, kv.m[8], ub[2])};
-      float val = RULE == MVF_RULE_SCIPY ? gather_scipy<T>(sm, bk, kv, rel) : gather_itk<T>(sm, bk, kv, rel);
+      float val;
+      if (RULE == MVF_RULE_SCIPY) val = bk.interior ? gather_scipy<true>(sm, bk, kv, rel) : gather_scipy<false>(sm, bk, kv, rel);
+      else val = gather_itk(sm, bk, kv, rel);
       if (sizeof(T) == 2) r[k] = (T)(RULE == MVF_RULE_SCIPY ? round_half_up_u16(val) : clamp_trunc_u16(val));
       else r[k] = (T)val;
     }
@@ -435,7 +511,7 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const __grid_constant
   const int gz = z + A.org[0], gy = y + A.org[1], gx = x + A.org[2];
   float w[V][RX];
   if (A.normalise) {
-    thread_weights<V>(A.v, gz, gy, gx, w);
+    thread_weights<V>(A.v, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], gz, gy, gx, w);
   } else {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -445,7 +521,7 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const __grid_constant
 #pragma unroll
       for (int k = 0; k < RX; ++k) {
         double c[3] = {fma((double)k, kv.wm[2], cb[0]), fma((double)k, kv.wm[5], cb[1]), fma((double)k, kv.wm[8], cb[2])};
-        w[v][k] = kv.wmode == MVF_W_OFF ? 0.f : blend_field(kv, c);
+        w[v][k] = kv.wmode == MVF_W_OFF ? 0.f : blend_field_exact(kv, c);
       }
     }
   }
@@ -484,13 +560,20 @@ __global__ void __launch_bounds__(NT) fuse_weighted_kernel(const __grid_constant
         accf = fmaf(w, val, accf);
       }
       acc = sizeof(T) == 2 ? (acc & 0xFFFFu) : min(acc, 65535u);
-    } else {  // np.mean(views, 0) -> float64 mean, clip, truncate (mv:4909-4912)
-      double s = 0.0;
-      for (int v = 0; v < A.nviews; ++v) s += (double)to_float(reinterpret_cast<const T*>(A.views[v])[i]);
-      s /= (double)A.nviews;
-      accf = (float)s;
-      s = fmin(fmax(s, 0.0), 65535.0);
-      acc = (uint32_t)s;
+    } else {  // np.mean(views, 0), clip, truncate (mv:4909-4912): float64 mean for uint16 views, float32 for float32
+      if (sizeof(T) == 2) {
+        double s = 0.0;
+        for (int v = 0; v < A.nviews; ++v) s += (double)to_float(reinterpret_cast<const T*>(A.views[v])[i]);
+        s /= (double)A.nviews;
+        accf = (float)s;
+        acc = (uint32_t)fmin(fmax(s, 0.0), 65535.0);
+      } else {
+        float s = 0.f;
+        for (int v = 0; v < A.nviews; ++v) s = __fadd_rn(s, to_float(reinterpret_cast<const T*>(A.views[v])[i]));
+        s = __fdiv_rn(s, (float)A.nviews);
+        accf = s;
+        acc = (uint32_t)fminf(fmaxf(s, 0.f), 65535.f);
+      }
     }
     A.out[i] = (uint16_t)acc;
     if (A.outf) A.outf[i] = accf;
@@ -528,7 +611,8 @@ static int to_kview(const mvf_view& h, KView& k, bool need_data) {
   return MVF_OK;
 }
 
-static size_t brick_bytes(const KView& k, size_t elem) {
+static size_t brick_bytes(const KView& k) {
+  const size_t elem = sizeof(float);
   size_t px = (size_t)k.be[2] | 1;
   size_t pz = ((size_t)k.be[1] * px) | 1;
   return ((size_t)k.be[0] * pz + 16) * elem;
@@ -551,12 +635,11 @@ template <int V>
 static int fuse_blend_v(const mvf_view* hv, uint16_t* out, float* outf, const int32_t dims[3], const int32_t org[3], cudaStream_t st) {
   FuseArgs<V> A;
   size_t smem = 0;
-  const size_t elem = hv[0].dtype == MVF_U16 ? 2 : 4;
   for (int v = 0; v < V; ++v) {
     int rc = to_kview(hv[v], A.v[v], true);
     if (rc) return rc;
     if (hv[v].dtype != hv[0].dtype) return fail(MVF_ERR_INVALID, "%s%s", "mvf_fuse_blend: all views must share one dtype");
-    size_t b = brick_bytes(A.v[v], elem);
+    size_t b = brick_bytes(A.v[v]);
     smem = b > smem ? b : smem;
   }
   if (smem > 220 * 1024) return fail(MVF_ERR_UNSUPPORTED, "%s%s", "mvf_fuse_blend: source brick of one tile exceeds shared memory (extreme down-scaling)");
@@ -636,7 +719,7 @@ extern "C" int mvf_affine_resample(const void* src, int dtype, const int32_t src
   if (rc) return rc;
   A.dst = dst;
   for (int d = 0; d < 3; ++d) { A.dims[d] = dst_dims[d]; A.org[d] = dst_origin[d]; }
-  size_t smem = brick_bytes(A.v, dtype == MVF_U16 ? 2 : 4);
+  size_t smem = brick_bytes(A.v);
   if (smem > 220 * 1024) return fail(MVF_ERR_UNSUPPORTED, "%s%s", "mvf_affine_resample: source brick of one tile exceeds shared memory (extreme down-scaling)");
   cudaStream_t st = as_stream(stream);
 #define LAUNCH(T, R)                                                                                   \
