@@ -2,19 +2,23 @@
 // sum) for sm_100a.  Reference arithmetic: mvregfus/multiview.py:1458-1634 (scipy path), 6797-6877 (ITK
 // path), 3469-3633 (blending weights), 4291-4317/4434-4439 (DCT weight upsampling), 4904-4912 (fusion).
 //
-// Work decomposition: one CTA per 8x8x32 (z,y,x) output tile, 256 threads, each thread owns a run of 8
-// consecutive x voxels (16-byte uint16 / 2x16-byte float32 stores).  For every view the CTA stages the
-// source brick hit by the tile (bounding box of the tile's affine footprint) in shared memory with
-// coalesced row loads, then gathers the 8 trilinear taps from shared memory, so the access pattern of a
-// rotated view never reaches L1/L2.  Blending weights are analytic (three 200-entry 1-D profiles per view)
-// and stay in registers until the sum over views is known; nothing but the views is read from HBM and
-// nothing but the fused volume is written.
+// Work decomposition: one CTA per 8x8x32 (z,y,x) output tile, 256 threads = 8 warps.  A warp owns one y row
+// of the tile, its lanes own 32 consecutive x voxels (coalesced 64-byte stores, conflict-free shared-memory
+// gathers for axis-aligned views because all shared-memory pitches are odd), and every thread walks the 8 z
+// planes of the tile.  For every view the CTA stages the source brick hit by the tile (bounding box of the
+// tile's affine footprint) in shared memory with 16-byte coalesced loads, converted to float32 once, then
+// gathers the 8 trilinear taps from shared memory, so the access pattern of a rotated view never reaches
+// L1/L2.  Blending weights are analytic (three 200-entry 1-D profiles per view) and wait in shared memory
+// until the sum over views is known; nothing but the views is read from HBM and nothing but the fused volume
+// is written.  The view loop is a real loop (the first version unrolled it and stalled on instruction fetch:
+// profiles/r01/fuse_blend_v2_ncu.md).
 #include "common.cuh"
 
 namespace mvf {
 
-constexpr int TZ = 8, TY = 8, TX = 32, RX = 8, NT = 256;
-static_assert(TZ * TY * (TX / RX) == NT, "tile/thread mapping");
+constexpr int TZ = 8, TY = 8, TX = 32, NT = 256;
+constexpr int TILE_VOX = TZ * TY * TX;
+static_assert(TY * TX == NT, "one thread per (y,x) column of the tile");
 
 struct KView {
   const void* data;
@@ -27,34 +31,34 @@ struct KView {
   int cd[3];
   int one_lo[3], one_hi[3];
   int wmode;
+  int vec;    // 16-byte aligned rows: vectorised staging allowed
   int be[3];  // host-computed upper bound of the brick extents (shared-memory sizing)
 };
 
-template <int V>
-struct FuseArgs {
-  KView v[V];
-  uint16_t* out;
-  float* outf;
+struct KArgs {
+  KView v[MVF_MAX_VIEWS];
+  int nviews;
+  int rule;
+  int normalise;
+  void* out;      // fused uint16 / resampled view / weights (float32, view-major)
+  float* outf;    // optional float32 pre-truncation sum
   int dims[3];
   int org[3];
 };
 
-struct ResampleArgs {
-  KView v;
-  void* dst;
-  int dims[3];
-  int org[3];
+enum { WT_ZERO = 0, WT_ONE = 1, WT_RAMP = 2, WT_EDGE = 3 };
+
+// Per-tile, per-view geometry, computed once per CTA (thread v handles view v) and kept in shared memory.
+struct TileView {
+  int b0[3];   // view index of brick element (0,0,0); may be negative (zero filled)
+  int e[3];    // extents
+  int px, pz;  // shared-memory pitches (elements), both odd
+  int skip;      // brick does not intersect the view
+  int interior;  // every voxel of the tile maps inside [0, n-1]: no per-voxel boundary test
+  int wclass;    // WT_*
 };
 
-struct Brick {
-  int b0[3];  // view index of brick element (0,0,0); may be negative (zero filled)
-  int e[3];   // extents
-  int px, pz; // shared-memory pitches (elements)
-  bool skip;      // brick does not intersect the view
-  bool interior;  // every voxel of the tile maps strictly inside [0, n-1]: no per-voxel boundary test
-};
-
-// Bounding box, in the index space of an affine map, of the voxels of one tile (fp64).
+// Bounding box, in the index space of an affine map, of the voxels of one tile (fp64), slightly inflated.
 __device__ __forceinline__ void tile_bbox(const double* m, const double* o, int z0, int y0, int x0, double lo[3], double hi[3]) {
   const int T[3] = {TZ - 1, TY - 1, TX - 1};
 #pragma unroll
@@ -71,46 +75,106 @@ __device__ __forceinline__ void tile_bbox(const double* m, const double* o, int 
   }
 }
 
-__device__ __forceinline__ Brick tile_brick(const KView& kv, int z0, int y0, int x0) {
-  Brick b;
+// Classify a tile against a view's blending field: every voxel outside the field (weight 0), every voxel
+// on the all-ones plateau (weight 1), fully inside the field (fast float32 path) or touching its rim.
+__device__ __forceinline__ int classify_tile(const KView& kv, int z0, int y0, int x0) {
+  if (kv.wmode == MVF_W_OFF) return WT_ZERO;
   double lo[3], hi[3];
-  tile_bbox(kv.m, kv.o, z0, y0, x0, lo, hi);
-  bool skip = false, interior = true;
+  tile_bbox(kv.wm, kv.wo, z0, y0, x0, lo, hi);
+  bool zero = false, one = true, ramp = true;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    int i0 = __double2int_rd(lo[d]);
-    int i1 = __double2int_rd(hi[d]) + 1;
-    b.b0[d] = i0;
-    int e = i1 - i0 + 1;
-    b.e[d] = e < kv.be[d] ? e : kv.be[d];
-    if (i1 < 0 || i0 > kv.n[d] - 1) skip = true;
-    if (!(lo[d] >= 0.0 && hi[d] <= (double)(kv.n[d] - 1))) interior = false;
+    zero = zero || (hi[d] < -0.5) || (lo[d] >= (double)MVF_SIG_N - 0.5);
+    one = one && (lo[d] >= (double)kv.one_lo[d]) && (hi[d] < (double)kv.one_hi[d]);
+    ramp = ramp && (lo[d] >= 0.0) && (hi[d] < (double)(MVF_SIG_N - 1));
   }
-  b.px = b.e[2] | 1;
-  b.pz = (b.e[1] * b.px) | 1;
-  b.skip = skip;
-  b.interior = interior;
-  return b;
+  return zero ? WT_ZERO : (one ? WT_ONE : (ramp ? WT_RAMP : WT_EDGE));
 }
+
+template <int ELEM>
+__device__ __forceinline__ void make_tile_view(const KView& kv, int z0, int y0, int x0, bool need_data, TileView& t) {
+  constexpr int VEC = 16 / ELEM;
+  t.skip = 1;
+  t.interior = 0;
+  if (need_data) {
+    double lo[3], hi[3];
+    tile_bbox(kv.m, kv.o, z0, y0, x0, lo, hi);
+    int skip = 0, interior = 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      int i0 = __double2int_rd(lo[d]);
+      int i1 = __double2int_rd(hi[d]) + 1;
+      if (i1 < 0 || i0 > kv.n[d] - 1) skip = 1;
+      if (!(lo[d] >= 0.0 && hi[d] <= (double)(kv.n[d] - 1))) interior = 0;
+      int e = i1 - i0 + 1;
+      if (d == 2 && kv.vec) {  // align the brick rows to 16 bytes of the source
+        int a0 = i0 & ~(VEC - 1);
+        e = (i1 - a0 + VEC) & ~(VEC - 1);
+        i0 = a0;
+      }
+      t.b0[d] = i0;
+      t.e[d] = e < kv.be[d] ? e : kv.be[d];
+    }
+    t.px = t.e[2] | 1;
+    t.pz = (t.e[1] * t.px) | 1;
+    t.skip = skip;
+    t.interior = interior;
+  }
+  t.wclass = classify_tile(kv, z0, y0, x0);
+}
+
+struct FastDiv {
+  unsigned m, d;
+  __device__ __forceinline__ explicit FastDiv(unsigned div) : m(div > 1 ? 0xFFFFFFFFu / div + 1u : 0u), d(div) {}
+  __device__ __forceinline__ unsigned div(unsigned x) const { return d > 1 ? __umulhi(x, m) : x; }  // exact for x*d < 2^32
+};
 
 // Cooperative, coalesced staging of the brick into shared memory as float32; out-of-volume elements are 0.
 template <typename T>
-__device__ __forceinline__ void stage_brick(const KView& kv, const Brick& bk, float* sm) {
+__device__ __forceinline__ void stage_brick(const KView& kv, const TileView& t, float* sm) {
   const T* __restrict__ src = reinterpret_cast<const T*>(kv.data);
-  const unsigned ex = bk.e[2], ey = bk.e[1];
-  const unsigned total = bk.e[0] * ey * ex;
-  const unsigned mx = 0xFFFFFFFFu / ex + 1u;   // exact quotient for i*ex < 2^32
-  const unsigned my = 0xFFFFFFFFu / ey + 1u;
-  for (unsigned i = threadIdx.x; i < total; i += NT) {
-    unsigned row = __umulhi(i, mx);
-    unsigned ix = i - row * ex;
-    unsigned iz = __umulhi(row, my);
-    unsigned iy = row - iz * ey;
-    int gz = bk.b0[0] + (int)iz, gy = bk.b0[1] + (int)iy, gx = bk.b0[2] + (int)ix;
-    float v = 0.f;
-    if ((unsigned)gz < (unsigned)kv.n[0] && (unsigned)gy < (unsigned)kv.n[1] && (unsigned)gx < (unsigned)kv.n[2])
-      v = to_float<T>(__ldg(src + ((size_t)gz * kv.n[1] + gy) * kv.n[2] + gx));
-    sm[iz * bk.pz + iy * bk.px + ix] = v;
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const unsigned ey = t.e[1];
+  const FastDiv dy(ey);
+  if (kv.vec) {
+    const unsigned cpr = t.e[2] / VEC;  // 16-byte chunks per brick row
+    const unsigned total = t.e[0] * ey * cpr;
+    const FastDiv dc(cpr);
+    for (unsigned i = threadIdx.x; i < total; i += NT) {
+      unsigned row = dc.div(i);
+      unsigned c = i - row * cpr;
+      unsigned iz = dy.div(row);
+      unsigned iy = row - iz * ey;
+      int gz = t.b0[0] + (int)iz, gy = t.b0[1] + (int)iy, gx = t.b0[2] + (int)c * VEC;
+      float* dst = sm + iz * t.pz + iy * t.px + c * VEC;
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if ((unsigned)gz < (unsigned)kv.n[0] && (unsigned)gy < (unsigned)kv.n[1] && (unsigned)gx < (unsigned)kv.n[2])
+        q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)gz * kv.n[1] + gy) * kv.n[2] + gx));
+      if (sizeof(T) == 4) {
+        dst[0] = __uint_as_float(q.x); dst[1] = __uint_as_float(q.y);
+        dst[2] = __uint_as_float(q.z); dst[3] = __uint_as_float(q.w);
+      } else {
+        dst[0] = u16_to_float(q.x & 0xFFFFu); dst[1] = u16_to_float(q.x >> 16);
+        dst[2] = u16_to_float(q.y & 0xFFFFu); dst[3] = u16_to_float(q.y >> 16);
+        dst[4] = u16_to_float(q.z & 0xFFFFu); dst[5] = u16_to_float(q.z >> 16);
+        dst[6] = u16_to_float(q.w & 0xFFFFu); dst[7] = u16_to_float(q.w >> 16);
+      }
+    }
+  } else {
+    const unsigned ex = t.e[2];
+    const unsigned total = t.e[0] * ey * ex;
+    const FastDiv dx(ex);
+    for (unsigned i = threadIdx.x; i < total; i += NT) {
+      unsigned row = dx.div(i);
+      unsigned ix = i - row * ex;
+      unsigned iz = dy.div(row);
+      unsigned iy = row - iz * ey;
+      int gz = t.b0[0] + (int)iz, gy = t.b0[1] + (int)iy, gx = t.b0[2] + (int)ix;
+      float v = 0.f;
+      if ((unsigned)gz < (unsigned)kv.n[0] && (unsigned)gy < (unsigned)kv.n[1] && (unsigned)gx < (unsigned)kv.n[2])
+        v = to_float<T>(__ldg(src + ((size_t)gz * kv.n[1] + gy) * kv.n[2] + gx));
+      sm[iz * t.pz + iy * t.px + ix] = v;
+    }
   }
 }
 
@@ -143,21 +207,20 @@ __device__ __forceinline__ float lerp8(const float* p, int ox, int oy, int oz, f
 // Trilinear value at brick-relative coordinate rel (float64), scipy 'constant' rule: 0 when the view
 // coordinate is outside [0, n-1] (ni_interpolation.c NI_GeometricTransform, mode constant).
 template <bool INTERIOR>
-__device__ __forceinline__ float gather_scipy(const float* sm, const Brick& bk, const KView& kv, const double rel[3]) {
+__device__ __forceinline__ float gather_scipy(const float* sm, int px, int pz, const double rel[3], const double lo[3], const double hi[3]) {
   int r[3], neg[3];
   float w[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) split_nearest(rel[d], r[d], w[d], neg[d]);
-  const float* p = sm + r[0] * bk.pz + r[1] * bk.px + r[2];
+  const float* p = sm + r[0] * pz + r[1] * px + r[2];
   const int ox = 1 | neg[2];
-  const int oy = (bk.px ^ neg[1]) - neg[1];
-  const int oz = (bk.pz ^ neg[0]) - neg[0];
+  const int oy = (px ^ neg[1]) - neg[1];
+  const int oz = (pz ^ neg[0]) - neg[0];
   float val = lerp8(p, ox, oy, oz, w[2], w[1], w[0]);
   if (!INTERIOR) {
     bool inside = true;
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-      inside = inside && (rel[d] >= -(double)bk.b0[d]) && (rel[d] <= (double)(kv.n[d] - 1 - bk.b0[d]));
+    for (int d = 0; d < 3; ++d) inside = inside && (rel[d] >= lo[d]) && (rel[d] <= hi[d]);
     val = inside ? val : 0.f;
   }
   return val;
@@ -165,21 +228,21 @@ __device__ __forceinline__ float gather_scipy(const float* sm, const Brick& bk, 
 
 // ITK rule: valid iff -0.5 <= u < n-0.5 per axis, neighbours clamped to the edge, outside -> 0
 // (itk::LinearInterpolateImageFunction / ResampleImageFilter).
-__device__ __forceinline__ float gather_itk(const float* sm, const Brick& bk, const KView& kv, const double rel[3]) {
+__device__ __forceinline__ float gather_itk(const float* sm, const TileView& t, const KView& kv, const double rel[3]) {
   int off[3], base = 0;
   float w[3];
   bool inside = true;
-  const int stride[3] = {bk.pz, bk.px, 1};
+  const int stride[3] = {t.pz, t.px, 1};
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    double u = rel[d] + (double)bk.b0[d];
+    double u = rel[d] + (double)t.b0[d];
     inside = inside && (u >= -0.5) && (u < (double)kv.n[d] - 0.5);
     int r, neg;
     split_nearest(u, r, w[d], neg);
     int near = max(0, min(r, kv.n[d] - 1));
     int far = max(0, min(r + (1 | neg), kv.n[d] - 1));
-    int ln = max(0, min(near - bk.b0[d], bk.e[d] - 1));
-    int lf = max(0, min(far - bk.b0[d], bk.e[d] - 1));
+    int ln = max(0, min(near - t.b0[d], t.e[d] - 1));
+    int lf = max(0, min(far - t.b0[d], t.e[d] - 1));
     base += ln * stride[d];
     off[d] = (lf - ln) * stride[d];
   }
@@ -188,24 +251,6 @@ __device__ __forceinline__ float gather_itk(const float* sm, const Brick& bk, co
 }
 
 // ---- blending field ------------------------------------------------------------------------------
-enum { WT_ZERO = 0, WT_ONE = 1, WT_RAMP = 2, WT_EDGE = 3 };
-
-// Classify a tile against a view's blending field: every voxel outside the field (weight 0), every voxel
-// on the all-ones plateau (weight 1), fully inside the field (fast float32 path) or touching its rim.
-__device__ __forceinline__ int classify_tile(const KView& kv, int z0, int y0, int x0) {
-  if (kv.wmode == MVF_W_OFF) return WT_ZERO;
-  double lo[3], hi[3];
-  tile_bbox(kv.wm, kv.wo, z0, y0, x0, lo, hi);
-  bool zero = false, one = true, ramp = true;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    zero = zero || (hi[d] < -0.5) || (lo[d] >= (double)MVF_SIG_N - 0.5);
-    one = one && (lo[d] >= (double)kv.one_lo[d]) && (hi[d] < (double)kv.one_hi[d]);
-    ramp = ramp && (lo[d] >= 0.0) && (hi[d] < (double)(MVF_SIG_N - 1));
-  }
-  return zero ? WT_ZERO : (one ? WT_ONE : (ramp ? WT_RAMP : WT_EDGE));
-}
-
 __device__ __forceinline__ float field_lerp(const float* f, int i0, int i1, int i2, int j0, int j1, int j2, float t0, float t1, float t2) {
   float a0 = __ldg(f + i0), a1 = __ldg(f + j0);
   float b0 = __ldg(f + MVF_SIG_N + i1), b1 = __ldg(f + MVF_SIG_N + j1);
@@ -224,7 +269,8 @@ __device__ __forceinline__ float field_lerp(const float* f, int i0, int i1, int 
 
 // ITK-linear sample of the analytic blending field min(f_z[i], f_y[j], f_x[k]) at continuous field index c
 // (exact float64 index arithmetic; used on tiles that touch the rim of the field).
-__device__ __forceinline__ float blend_field_exact(const KView& kv, const double c[3]) {
+__device__ __noinline__ float blend_field_exact(const KView& kv, double c0, double c1, double c2) {
+  const double c[3] = {c0, c1, c2};
   int i0[3];
   float t[3];
   bool inside = true, ones = true;
@@ -246,7 +292,8 @@ __device__ __forceinline__ float blend_field_exact(const KView& kv, const double
 }
 
 // ITK-linear sample of a small float32 grid in global memory (coarse DCT weights, mv:4304-4311).
-__device__ __forceinline__ float coarse_sample(const KView& kv, const double c[3]) {
+__device__ __noinline__ float coarse_sample(const KView& kv, double c0, double c1, double c2) {
+  const double c[3] = {c0, c1, c2};
   int i0[3], i1[3];
   float t[3];
   bool inside = true;
@@ -283,255 +330,250 @@ __device__ __forceinline__ void affine_base(const double* m, const double* o, in
     out[d] = fma(m[d * 3 + 2], (double)x, fma(m[d * 3 + 1], (double)y, fma(m[d * 3 + 0], (double)z, o[d])));
 }
 
-// Blending (x coarse DCT) weights of the RX voxels of a thread for all V views, normalised exactly like
-// the reference: w_v / sum_v w_v in float32 with a 0 -> 1 guard (mv:3627-3631), and for the DCT mode
-// coarse_v * that, normalised again (mv:4317, 4434-4439).  (tz0,ty0,tx0) is the fused-frame index of the
-// tile origin, (gz,gy,gx) of the thread's first voxel.
-template <int V>
-__device__ __forceinline__ void thread_weights(const KView* kvs, int tz0, int ty0, int tx0, int gz, int gy, int gx,
-                                               float (&w)[V][RX]) {
-  float wsum[RX];
+// Raw (un-normalised) blending weights of the TZ voxels of a thread (fused index (gz+k, gy, gx)) for one view.
+__device__ __forceinline__ void column_blend(const KView& kv, int cls, int gz, int gy, int gx, float (&w)[TZ]) {
+  if (cls == WT_ZERO || cls == WT_ONE) {
+    const float c = cls == WT_ONE ? 1.f : 0.f;
 #pragma unroll
-  for (int k = 0; k < RX; ++k) wsum[k] = 0.f;
-  bool dct = false;
+    for (int k = 0; k < TZ; ++k) w[k] = c;
+    return;
+  }
+  double cb[3];
+  affine_base(kv.wm, kv.wo, gz, gy, gx, cb);
+  if (cls == WT_RAMP) {
+    // float32 steps on a float64 base: |error| < 1e-6 field voxels, i.e. < 3e-7 in the weight
+    int ci[3];
+    float cf[3], cm[3];
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const KView& kv = kvs[v];
-    const int cls = classify_tile(kv, tz0, ty0, tx0);  // CTA-uniform
-    if (cls == WT_ZERO) {
-#pragma unroll
-      for (int k = 0; k < RX; ++k) w[v][k] = 0.f;
-      continue;
+    for (int d = 0; d < 3; ++d) {
+      ci[d] = __double2int_rd(cb[d]);
+      cf[d] = (float)(cb[d] - (double)ci[d]);
+      cm[d] = (float)kv.wm[d * 3 + 0];
     }
-    dct = dct || (kv.wmode == MVF_W_BLEND_DCT);
-    if (cls == WT_ONE) {
 #pragma unroll
-      for (int k = 0; k < RX; ++k) { w[v][k] = 1.f; wsum[k] += 1.f; }
-      continue;
-    }
-    double cb[3];
-    affine_base(kv.wm, kv.wo, gz, gy, gx, cb);
-    if (cls == WT_RAMP) {
-      // float32 increments on a float64 base: |error| < 1e-6 field voxels, i.e. < 3e-7 in the weight
-      int ci[3];
-      float cf[3], cm[3];
+    for (int k = 0; k < TZ; ++k) {
+      int i0[3];
+      float t[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        ci[d] = __double2int_rd(cb[d]);
-        cf[d] = (float)(cb[d] - (double)ci[d]);
-        cm[d] = (float)kv.wm[d * 3 + 2];
+        float c = fmaf((float)k, cm[d], cf[d]);
+        float y = __fadd_rd(c, MAGIC32);
+        t[d] = c - (y - MAGIC32);
+        i0[d] = ci[d] + (__float_as_int(y) - 0x4B400000);
+        i0[d] = max(0, min(i0[d], MVF_SIG_N - 2));  // rounding guard at the bbox limits
       }
-#pragma unroll
-      for (int k = 0; k < RX; ++k) {
-        int i0[3];
-        float t[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          float c = fmaf((float)k, cm[d], cf[d]);
-          float y = __fadd_rd(c, MAGIC32);
-          t[d] = c - (y - MAGIC32);
-          i0[d] = ci[d] + (__float_as_int(y) - 0x4B400000);
-          i0[d] = max(0, min(i0[d], MVF_SIG_N - 2));  // rounding guard at the bbox limits
-        }
-        float wv = field_lerp(kv.prof, i0[0], i0[1], i0[2], i0[0] + 1, i0[1] + 1, i0[2] + 1, t[0], t[1], t[2]);
-        w[v][k] = wv;
-        wsum[k] += wv;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < RX; ++k) {
-        double c[3] = {fma((double)k, kv.wm[2], cb[0]), fma((double)k, kv.wm[5], cb[1]), fma((double)k, kv.wm[8], cb[2])};
-        w[v][k] = blend_field_exact(kv, c);
-        wsum[k] += w[v][k];
-      }
+      w[k] = field_lerp(kv.prof, i0[0], i0[1], i0[2], i0[0] + 1, i0[1] + 1, i0[2] + 1, t[0], t[1], t[2]);
     }
-  }
-#pragma unroll
-  for (int k = 0; k < RX; ++k) {
-    float d = wsum[k] == 0.f ? 1.f : wsum[k];
-#pragma unroll
-    for (int v = 0; v < V; ++v) w[v][k] = __fdiv_rn(w[v][k], d);
-  }
-  if (dct) {
-#pragma unroll
-    for (int k = 0; k < RX; ++k) wsum[k] = 0.f;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const KView& kv = kvs[v];
-      if (kv.wmode != MVF_W_BLEND_DCT) continue;
-#pragma unroll
-      for (int k = 0; k < RX; ++k) {
-        float cw = 0.f;
-        if (w[v][k] != 0.f) {
-          double c[3] = {fma(kv.cs[0], (double)gz, kv.co[0]), fma(kv.cs[1], (double)gy, kv.co[1]),
-                         fma(kv.cs[2], (double)(gx + k), kv.co[2])};
-          cw = coarse_sample(kv, c);
-        }
-        w[v][k] = cw * w[v][k];
-        wsum[k] += w[v][k];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < RX; ++k) {
-      float d = wsum[k] == 0.f ? 1.f : wsum[k];
-#pragma unroll
-      for (int v = 0; v < V; ++v) w[v][k] = __fdiv_rn(w[v][k], d);
-    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < TZ; ++k)
+      w[k] = blend_field_exact(kv, fma((double)k, kv.wm[0], cb[0]), fma((double)k, kv.wm[3], cb[1]), fma((double)k, kv.wm[6], cb[2]));
   }
 }
 
-__device__ __forceinline__ void thread_voxel(int& lz, int& ly, int& lx) {
-  const int t = threadIdx.x;
-  lx = (t & 3) * RX;
-  ly = (t >> 2) & 7;
-  lz = t >> 5;
+// Weights of all views for the thread's column, normalised exactly like the reference: w_v / sum_v w_v in
+// float32 with a 0 -> 1 guard (mv:3627-3631), and for the DCT mode coarse_v * that, normalised again
+// (mv:4317, 4434-4439).  Raw values go to wsm[v][k][tid]; the divisor of each voxel is returned in wsum.
+__device__ __forceinline__ void column_weights(const KArgs& A, const TileView* tv, float* wsm, int gz, int gy, int gx,
+                                               float (&wsum)[TZ]) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < TZ; ++k) wsum[k] = 0.f;
+  bool dct = false;
+  for (int v = 0; v < A.nviews; ++v) {
+    const KView& kv = A.v[v];
+    float w[TZ];
+    column_blend(kv, tv[v].wclass, gz, gy, gx, w);
+    dct = dct || (kv.wmode == MVF_W_BLEND_DCT);
+#pragma unroll
+    for (int k = 0; k < TZ; ++k) {
+      wsm[(v * TZ + k) * NT + tid] = w[k];
+      wsum[k] += w[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < TZ; ++k) wsum[k] = wsum[k] == 0.f ? 1.f : wsum[k];
+  if (dct) {
+    float wsum2[TZ];
+#pragma unroll
+    for (int k = 0; k < TZ; ++k) wsum2[k] = 0.f;
+    for (int v = 0; v < A.nviews; ++v) {
+      const KView& kv = A.v[v];
+#pragma unroll
+      for (int k = 0; k < TZ; ++k) {
+        float wn = __fdiv_rn(wsm[(v * TZ + k) * NT + tid], wsum[k]);
+        float cw = 0.f;
+        if (wn != 0.f && kv.wmode == MVF_W_BLEND_DCT)
+          cw = coarse_sample(kv, fma(kv.cs[0], (double)(gz + k), kv.co[0]), fma(kv.cs[1], (double)gy, kv.co[1]),
+                             fma(kv.cs[2], (double)gx, kv.co[2]));
+        wn = cw * wn;
+        wsm[(v * TZ + k) * NT + tid] = wn;
+        wsum2[k] += wn;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TZ; ++k) wsum[k] = wsum2[k] == 0.f ? 1.f : wsum2[k];
+  }
+}
+
+// Values of one view at the thread's TZ voxels (scipy rule), from the staged brick.
+template <bool INTERIOR>
+__device__ __forceinline__ void column_gather(const float* sm, const TileView& t, const KView& kv, int gz, int gy, int gx,
+                                              float (&val)[TZ]) {
+  double rel[3], step[3], lo[3], hi[3];
+  affine_base(kv.m, kv.o, gz, gy, gx, rel);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    rel[d] -= (double)t.b0[d];
+    step[d] = kv.m[d * 3 + 0];
+    lo[d] = -(double)t.b0[d];
+    hi[d] = (double)(kv.n[d] - 1 - t.b0[d]);
+  }
+  const int px = t.px, pz = t.pz;
+#pragma unroll
+  for (int k = 0; k < TZ; ++k) {
+    val[k] = gather_scipy<INTERIOR>(sm, px, pz, rel, lo, hi);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) rel[d] += step[d];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: fused single pass
 // ------------------------------------------------------------------------------------------------
-template <typename T, int V>
-__global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ FuseArgs<V> A) {
+template <typename T>
+__global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sm = reinterpret_cast<float*>(smem_raw);
+  __shared__ TileView tv[MVF_MAX_VIEWS];
+  float* wsm = reinterpret_cast<float*>(smem_raw);
+  float* sm = wsm + A.nviews * TILE_VOX;
   const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
-  int lz, ly, lx;
-  thread_voxel(lz, ly, lx);
-  const int z = z0 + lz, y = y0 + ly, x = x0 + lx;              // local (box) index
-  const int gz = z + A.org[0], gy = y + A.org[1], gx = x + A.org[2];  // fused-frame index
+  const int tid = threadIdx.x;
+  if (tid < A.nviews)
+    make_tile_view<sizeof(T)>(A.v[tid], z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], true, tv[tid]);
+  __syncthreads();
+  const int y = y0 + (tid >> 5), x = x0 + (tid & 31);                        // local (box) index
+  const int gz = z0 + A.org[0], gy = y + A.org[1], gx = x + A.org[2];        // fused-frame index of voxel k=0
 
-  float w[V][RX];
-  thread_weights<V>(A.v, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], gz, gy, gx, w);
+  float wsum[TZ];
+  column_weights(A, tv, wsm, gz, gy, gx, wsum);
 
-  uint32_t acc[RX];
-  float accf[RX];
+  uint32_t acc[TZ];
+  float accf[TZ];
 #pragma unroll
-  for (int k = 0; k < RX; ++k) { acc[k] = 0u; accf[k] = 0.f; }
+  for (int k = 0; k < TZ; ++k) { acc[k] = 0u; accf[k] = 0.f; }
 
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
+  for (int v = 0; v < A.nviews; ++v) {
+    const TileView& t = tv[v];
+    if (t.skip) continue;  // CTA-uniform
     const KView& kv = A.v[v];
-    const Brick bk = tile_brick(kv, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2]);
-    if (bk.skip) continue;  // CTA-uniform
     __syncthreads();
-    stage_brick<T>(kv, bk, sm);
+    stage_brick<T>(kv, t, sm);
     __syncthreads();
-    double ub[3];
-    affine_base(kv.m, kv.o, gz, gy, gx, ub);
+    float val[TZ];
+    if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, val);
+    else column_gather<false>(sm, t, kv, gz, gy, gx, val);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) ub[d] -= (double)bk.b0[d];
-#pragma unroll
-    for (int k = 0; k < RX; ++k) {
-      double rel[3] = {fma((double)k, kv.m[2], ub[0]), fma((double)k, kv.m[5], ub[1]), fma((double)k, kv.m[8], ub[2])};
-      float val = bk.interior ? gather_scipy<true>(sm, bk, kv, rel) : gather_scipy<false>(sm, bk, kv, rel);
-      if (sizeof(T) == 2) val = u16_to_float(round_half_up_u16(val));  // the transformed view is uint16 (mv:1626)
-      acc[k] += trunc_product_u16(w[v][k], val);
-      accf[k] = fmaf(w[v][k], val, accf[k]);
+    for (int k = 0; k < TZ; ++k) {
+      float wn = __fdiv_rn(wsm[(v * TZ + k) * NT + tid], wsum[k]);
+      float vv = val[k];
+      if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));  // the transformed view is uint16 (mv:1626)
+      acc[k] += trunc_product_u16(wn, vv);
+      accf[k] = fmaf(wn, vv, accf[k]);
     }
   }
 
-  if (z >= A.dims[0] || y >= A.dims[1]) return;
-  const size_t row = ((size_t)z * A.dims[1] + y) * A.dims[2];
-  uint32_t r[RX];
+  if (y >= A.dims[1] || x >= A.dims[2]) return;
+  uint16_t* out = reinterpret_cast<uint16_t*>(A.out);
 #pragma unroll
-  for (int k = 0; k < RX; ++k) r[k] = sizeof(T) == 2 ? (acc[k] & 0xFFFFu) : min(acc[k], 65535u);
-  if (x + RX <= A.dims[2] && (((row + x) & 7) == 0)) {
-    uint4 pk;
-    pk.x = r[0] | (r[1] << 16); pk.y = r[2] | (r[3] << 16); pk.z = r[4] | (r[5] << 16); pk.w = r[6] | (r[7] << 16);
-    *reinterpret_cast<uint4*>(A.out + row + x) = pk;
-  } else {
-#pragma unroll
-    for (int k = 0; k < RX; ++k) if (x + k < A.dims[2]) A.out[row + x + k] = (uint16_t)r[k];
-  }
-  if (A.outf) {
-#pragma unroll
-    for (int k = 0; k < RX; ++k) if (x + k < A.dims[2]) A.outf[row + x + k] = accf[k];
+  for (int k = 0; k < TZ; ++k) {
+    const int z = z0 + k;
+    if (z >= A.dims[0]) break;
+    const size_t idx = ((size_t)z * A.dims[1] + y) * A.dims[2] + x;
+    out[idx] = (uint16_t)(sizeof(T) == 2 ? (acc[k] & 0xFFFFu) : min(acc[k], 65535u));
+    if (A.outf) A.outf[idx] = accf[k];
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1: one view, same dtype out
 // ------------------------------------------------------------------------------------------------
-template <typename T, int RULE>
-__global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ ResampleArgs A) {
+template <typename T>
+__global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ TileView tv[1];
   float* sm = reinterpret_cast<float*>(smem_raw);
   const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
-  int lz, ly, lx;
-  thread_voxel(lz, ly, lx);
-  const int z = z0 + lz, y = y0 + ly, x = x0 + lx;
-  const int gz = z + A.org[0], gy = y + A.org[1], gx = x + A.org[2];
-  const KView& kv = A.v;
-  const Brick bk = tile_brick(kv, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2]);
-  T r[RX];
+  const int tid = threadIdx.x;
+  const KView& kv = A.v[0];
+  if (tid == 0) make_tile_view<sizeof(T)>(kv, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], true, tv[0]);
+  __syncthreads();
+  const TileView& t = tv[0];
+  const int y = y0 + (tid >> 5), x = x0 + (tid & 31);
+  const int gz = z0 + A.org[0], gy = y + A.org[1], gx = x + A.org[2];
+  float val[TZ];
 #pragma unroll
-  for (int k = 0; k < RX; ++k) r[k] = T(0);
-  if (!bk.skip) {
-    stage_brick<T>(kv, bk, sm);
+  for (int k = 0; k < TZ; ++k) val[k] = 0.f;
+  if (!t.skip) {
+    stage_brick<T>(kv, t, sm);
     __syncthreads();
-    double ub[3];
-    affine_base(kv.m, kv.o, gz, gy, gx, ub);
+    if (A.rule == MVF_RULE_SCIPY) {
+      if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, val);
+      else column_gather<false>(sm, t, kv, gz, gy, gx, val);
+    } else {
+      double rel[3];
+      affine_base(kv.m, kv.o, gz, gy, gx, rel);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) ub[d] -= (double)bk.b0[d];
+      for (int d = 0; d < 3; ++d) rel[d] -= (double)t.b0[d];
+#pragma unroll 1
+      for (int k = 0; k < TZ; ++k) {
+        val[k] = gather_itk(sm, t, kv, rel);
 #pragma unroll
-    for (int k = 0; k < RX; ++k) {
-      double rel[3] = {fma((double)k, kv.m[2], ub[0]), fma((double)k, kv.m[5], ub[1]), fma((double)k, kv.m[8], ub[2])};
-      float val;
-      if (RULE == MVF_RULE_SCIPY) val = bk.interior ? gather_scipy<true>(sm, bk, kv, rel) : gather_scipy<false>(sm, bk, kv, rel);
-      else val = gather_itk(sm, bk, kv, rel);
-      if (sizeof(T) == 2) r[k] = (T)(RULE == MVF_RULE_SCIPY ? round_half_up_u16(val) : clamp_trunc_u16(val));
-      else r[k] = (T)val;
-    }
-  }
-  if (z >= A.dims[0] || y >= A.dims[1]) return;
-  T* dst = reinterpret_cast<T*>(A.dst) + ((size_t)z * A.dims[1] + y) * A.dims[2];
-#pragma unroll
-  for (int k = 0; k < RX; ++k) if (x + k < A.dims[2]) dst[x + k] = r[k];
-}
-
-// ------------------------------------------------------------------------------------------------
-// blending weights on a grid (get_weights_simple), V volumes out
-// ------------------------------------------------------------------------------------------------
-template <int V>
-struct WeightArgs {
-  KView v[V];
-  float* out;
-  int dims[3];
-  int org[3];
-  int normalise;
-};
-
-template <int V>
-__global__ void __launch_bounds__(NT) blend_weights_kernel(const __grid_constant__ WeightArgs<V> A) {
-  const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
-  int lz, ly, lx;
-  thread_voxel(lz, ly, lx);
-  const int z = z0 + lz, y = y0 + ly, x = x0 + lx;
-  if (z >= A.dims[0] || y >= A.dims[1]) return;
-  const int gz = z + A.org[0], gy = y + A.org[1], gx = x + A.org[2];
-  float w[V][RX];
-  if (A.normalise) {
-    thread_weights<V>(A.v, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], gz, gy, gx, w);
-  } else {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const KView& kv = A.v[v];
-      double cb[3];
-      affine_base(kv.wm, kv.wo, gz, gy, gx, cb);
-#pragma unroll
-      for (int k = 0; k < RX; ++k) {
-        double c[3] = {fma((double)k, kv.wm[2], cb[0]), fma((double)k, kv.wm[5], cb[1]), fma((double)k, kv.wm[8], cb[2])};
-        w[v][k] = kv.wmode == MVF_W_OFF ? 0.f : blend_field_exact(kv, c);
+        for (int d = 0; d < 3; ++d) rel[d] += kv.m[d * 3 + 0];
       }
     }
   }
+  if (y >= A.dims[1] || x >= A.dims[2]) return;
+  T* dst = reinterpret_cast<T*>(A.out);
+#pragma unroll
+  for (int k = 0; k < TZ; ++k) {
+    const int z = z0 + k;
+    if (z >= A.dims[0]) break;
+    const size_t idx = ((size_t)z * A.dims[1] + y) * A.dims[2] + x;
+    if (sizeof(T) == 2) dst[idx] = (T)(A.rule == MVF_RULE_SCIPY ? round_half_up_u16(val[k]) : clamp_trunc_u16(val[k]));
+    else dst[idx] = (T)val[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// blending weights on a grid (get_weights_simple), V float32 volumes out
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) blend_weights_kernel(const __grid_constant__ KArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ TileView tv[MVF_MAX_VIEWS];
+  float* wsm = reinterpret_cast<float*>(smem_raw);
+  const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
+  const int tid = threadIdx.x;
+  if (tid < A.nviews)
+    make_tile_view<4>(A.v[tid], z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], false, tv[tid]);
+  __syncthreads();
+  const int y = y0 + (tid >> 5), x = x0 + (tid & 31);
+  const int gz = z0 + A.org[0], gy = y + A.org[1], gx = x + A.org[2];
+  float wsum[TZ];
+  column_weights(A, tv, wsm, gz, gy, gx, wsum);
+  if (y >= A.dims[1] || x >= A.dims[2]) return;
+  float* out = reinterpret_cast<float*>(A.out);
   const size_t vol = (size_t)A.dims[0] * A.dims[1] * A.dims[2];
-  const size_t row = ((size_t)z * A.dims[1] + y) * A.dims[2];
+  for (int v = 0; v < A.nviews; ++v) {
 #pragma unroll
-  for (int v = 0; v < V; ++v)
-#pragma unroll
-    for (int k = 0; k < RX; ++k)
-      if (x + k < A.dims[2]) A.out[v * vol + row + x + k] = w[v][k];
+    for (int k = 0; k < TZ; ++k) {
+      const int z = z0 + k;
+      if (z >= A.dims[0]) break;
+      float w = wsm[(v * TZ + k) * NT + tid];
+      if (A.normalise) w = __fdiv_rn(w, wsum[k]);
+      out[v * vol + ((size_t)z * A.dims[1] + y) * A.dims[2] + x] = w;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -602,62 +644,54 @@ static int to_kview(const mvf_view& h, KView& k, bool need_data) {
   k.wmode = h.weight_mode;
   if (k.wmode != MVF_W_OFF && !h.profiles) return fail(MVF_ERR_INVALID, "%s%s", "mvf_view.profiles is NULL but weight_mode != MVF_W_OFF");
   if (k.wmode == MVF_W_BLEND_DCT && !h.cgrid) return fail(MVF_ERR_INVALID, "%s%s", "mvf_view.cgrid is NULL but weight_mode == MVF_W_BLEND_DCT");
+  const int vecn = h.dtype == MVF_U16 ? 8 : 4;
+  k.vec = need_data && ((reinterpret_cast<uintptr_t>(h.data) & 15u) == 0) && (h.dims[2] % vecn == 0);
   const int T[3] = {TZ - 1, TY - 1, TX - 1};
   for (int d = 0; d < 3; ++d) {
     double ext = 0;
     for (int l = 0; l < 3; ++l) ext += fabs(h.matrix[d * 3 + l]) * T[l];
-    k.be[d] = (int)ceil(ext) + 4;
+    k.be[d] = (int)ceil(ext) + 4 + (d == 2 && k.vec ? 2 * vecn : 0);
   }
   return MVF_OK;
 }
 
 static size_t brick_bytes(const KView& k) {
-  const size_t elem = sizeof(float);
   size_t px = (size_t)k.be[2] | 1;
   size_t pz = ((size_t)k.be[1] * px) | 1;
-  return ((size_t)k.be[0] * pz + 16) * elem;
+  return ((size_t)k.be[0] * pz + 16) * sizeof(float);
 }
 
 static dim3 tile_grid(const int32_t dims[3]) {
   return dim3((dims[2] + TX - 1) / TX, (dims[1] + TY - 1) / TY, (dims[0] + TZ - 1) / TZ);
 }
 
-template <typename T, int V>
-static int launch_fuse(const FuseArgs<V>& A, size_t smem, cudaStream_t st) {
-  auto kern = fuse_blend_kernel<T, V>;
-  MVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<tile_grid(A.dims), NT, smem, st>>>(A);
-  MVF_LAUNCHED();
+static int fill_args(KArgs& A, int nviews, const mvf_view* hv, bool need_data, void* out, float* outf,
+                     const int32_t dims[3], const int32_t org[3], size_t* brick) {
+  memset(&A, 0, sizeof(A));
+  size_t smem = 0;
+  for (int v = 0; v < nviews; ++v) {
+    int rc = to_kview(hv[v], A.v[v], need_data);
+    if (rc) return rc;
+    if (need_data && hv[v].dtype != hv[0].dtype) return fail(MVF_ERR_INVALID, "%s%s", "all views of one call must share one dtype");
+    if (need_data) {
+      size_t b = brick_bytes(A.v[v]);
+      smem = b > smem ? b : smem;
+    }
+  }
+  A.nviews = nviews;
+  A.out = out;
+  A.outf = outf;
+  for (int d = 0; d < 3; ++d) { A.dims[d] = dims[d]; A.org[d] = org[d]; }
+  *brick = smem;
   return MVF_OK;
 }
 
-template <int V>
-static int fuse_blend_v(const mvf_view* hv, uint16_t* out, float* outf, const int32_t dims[3], const int32_t org[3], cudaStream_t st) {
-  FuseArgs<V> A;
-  size_t smem = 0;
-  for (int v = 0; v < V; ++v) {
-    int rc = to_kview(hv[v], A.v[v], true);
-    if (rc) return rc;
-    if (hv[v].dtype != hv[0].dtype) return fail(MVF_ERR_INVALID, "%s%s", "mvf_fuse_blend: all views must share one dtype");
-    size_t b = brick_bytes(A.v[v]);
-    smem = b > smem ? b : smem;
-  }
-  if (smem > 220 * 1024) return fail(MVF_ERR_UNSUPPORTED, "%s%s", "mvf_fuse_blend: source brick of one tile exceeds shared memory (extreme down-scaling)");
-  A.out = out; A.outf = outf;
-  for (int d = 0; d < 3; ++d) { A.dims[d] = dims[d]; A.org[d] = org[d]; }
-  return hv[0].dtype == MVF_U16 ? launch_fuse<uint16_t, V>(A, smem, st) : launch_fuse<float, V>(A, smem, st);
-}
-
-template <int V>
-static int blend_weights_v(const mvf_view* hv, float* out, const int32_t dims[3], const int32_t org[3], int normalise, cudaStream_t st) {
-  WeightArgs<V> A;
-  for (int v = 0; v < V; ++v) {
-    int rc = to_kview(hv[v], A.v[v], false);
-    if (rc) return rc;
-  }
-  A.out = out; A.normalise = normalise;
-  for (int d = 0; d < 3; ++d) { A.dims[d] = dims[d]; A.org[d] = org[d]; }
-  blend_weights_kernel<V><<<tile_grid(dims), NT, 0, st>>>(A);
+template <typename K>
+static int launch_tiles(K kern, const KArgs& A, size_t smem, cudaStream_t st) {
+  if (smem > 220 * 1024)
+    return fail(MVF_ERR_UNSUPPORTED, "%s%s", "source brick of one output tile exceeds shared memory (extreme down-scaling)");
+  MVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<tile_grid(A.dims), NT, smem, st>>>(A);
   MVF_LAUNCHED();
   return MVF_OK;
 }
@@ -666,28 +700,18 @@ static int blend_weights_v(const mvf_view* hv, float* out, const int32_t dims[3]
 
 using namespace mvf;
 
-#define MVF_DISPATCH_V(n, CALL)                \
-  switch (n) {                                 \
-    case 1: return CALL(1);                    \
-    case 2: return CALL(2);                    \
-    case 3: return CALL(3);                    \
-    case 4: return CALL(4);                    \
-    case 5: return CALL(5);                    \
-    case 6: return CALL(6);                    \
-    case 7: return CALL(7);                    \
-    case 8: return CALL(8);                    \
-    default: break;                            \
-  }
-
 extern "C" int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* out, float* out_f32,
                               const int32_t out_dims[3], const int32_t out_origin[3], void* stream) {
   MVF_CHECK_ARG(nviews >= 1 && nviews <= MVF_MAX_VIEWS, "nviews must be in [1, MVF_MAX_VIEWS]");
   MVF_CHECK_ARG(host_views && out && out_dims && out_origin, "NULL argument");
   MVF_CHECK_ARG(out_dims[0] > 0 && out_dims[1] > 0 && out_dims[2] > 0, "out_dims must be positive");
-#define CALL(V) fuse_blend_v<V>(host_views, out, out_f32, out_dims, out_origin, as_stream(stream))
-  MVF_DISPATCH_V(nviews, CALL)
-#undef CALL
-  return fail(MVF_ERR_INVALID, "%s%s", "mvf_fuse_blend: bad nviews");
+  KArgs A;
+  size_t brick;
+  int rc = fill_args(A, nviews, host_views, true, out, out_f32, out_dims, out_origin, &brick);
+  if (rc) return rc;
+  const size_t smem = brick + (size_t)nviews * TILE_VOX * sizeof(float);
+  return host_views[0].dtype == MVF_U16 ? launch_tiles(fuse_blend_kernel<uint16_t>, A, smem, as_stream(stream))
+                                        : launch_tiles(fuse_blend_kernel<float>, A, smem, as_stream(stream));
 }
 
 extern "C" int mvf_blend_weights(int nviews, const mvf_view* host_views, float* weights_out, const int32_t dims[3],
@@ -695,10 +719,12 @@ extern "C" int mvf_blend_weights(int nviews, const mvf_view* host_views, float* 
   MVF_CHECK_ARG(nviews >= 1 && nviews <= MVF_MAX_VIEWS, "nviews must be in [1, MVF_MAX_VIEWS]");
   MVF_CHECK_ARG(host_views && weights_out && dims && origin, "NULL argument");
   MVF_CHECK_ARG(dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "dims must be positive");
-#define CALL(V) blend_weights_v<V>(host_views, weights_out, dims, origin, normalise, as_stream(stream))
-  MVF_DISPATCH_V(nviews, CALL)
-#undef CALL
-  return fail(MVF_ERR_INVALID, "%s%s", "mvf_blend_weights: bad nviews");
+  KArgs A;
+  size_t brick;
+  int rc = fill_args(A, nviews, host_views, false, weights_out, nullptr, dims, origin, &brick);
+  if (rc) return rc;
+  A.normalise = normalise;
+  return launch_tiles(blend_weights_kernel, A, (size_t)nviews * TILE_VOX * sizeof(float), as_stream(stream));
 }
 
 extern "C" int mvf_affine_resample(const void* src, int dtype, const int32_t src_dims[3], const double matrix[9],
@@ -714,25 +740,13 @@ extern "C" int mvf_affine_resample(const void* src, int dtype, const int32_t src
   for (int d = 0; d < 3; ++d) { h.dims[d] = src_dims[d]; h.offset[d] = offset[d]; }
   for (int i = 0; i < 9; ++i) h.matrix[i] = matrix[i];
   h.weight_mode = MVF_W_OFF;
-  ResampleArgs A;
-  int rc = to_kview(h, A.v, true);
+  KArgs A;
+  size_t brick;
+  int rc = fill_args(A, 1, &h, true, dst, nullptr, dst_dims, dst_origin, &brick);
   if (rc) return rc;
-  A.dst = dst;
-  for (int d = 0; d < 3; ++d) { A.dims[d] = dst_dims[d]; A.org[d] = dst_origin[d]; }
-  size_t smem = brick_bytes(A.v);
-  if (smem > 220 * 1024) return fail(MVF_ERR_UNSUPPORTED, "%s%s", "mvf_affine_resample: source brick of one tile exceeds shared memory (extreme down-scaling)");
-  cudaStream_t st = as_stream(stream);
-#define LAUNCH(T, R)                                                                                   \
-  do {                                                                                                 \
-    auto kern = resample_kernel<T, R>;                                                                 \
-    MVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    kern<<<tile_grid(dst_dims), NT, smem, st>>>(A);                                                    \
-    MVF_LAUNCHED();                                                                                    \
-  } while (0)
-  if (dtype == MVF_U16) { if (rule == MVF_RULE_SCIPY) LAUNCH(uint16_t, MVF_RULE_SCIPY); else LAUNCH(uint16_t, MVF_RULE_ITK); }
-  else                  { if (rule == MVF_RULE_SCIPY) LAUNCH(float, MVF_RULE_SCIPY);    else LAUNCH(float, MVF_RULE_ITK); }
-#undef LAUNCH
-  return MVF_OK;
+  A.rule = rule;
+  return dtype == MVF_U16 ? launch_tiles(resample_kernel<uint16_t>, A, brick, as_stream(stream))
+                          : launch_tiles(resample_kernel<float>, A, brick, as_stream(stream));
 }
 
 extern "C" int mvf_fuse_weighted(int nviews, const void* const* host_view_ptrs, int dtype,
