@@ -74,7 +74,7 @@ def load():
     global _lib
     with _lock:
         if _lib is None:
-            path = _build.lib_path()
+            path = os.environ.get("MVF_LIB") or _build.lib_path()  # MVF_LIB: kernel-variant experiments
             if not os.path.exists(path):
                 if os.environ.get("MVF_AUTOBUILD") == "1":
                     _build.build()

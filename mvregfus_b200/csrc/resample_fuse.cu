@@ -19,6 +19,7 @@ namespace mvf {
 constexpr int TZ = 8, TY = 8, TX = 32, NT = 256;
 constexpr int TILE_VOX = TZ * TY * TX;
 static_assert(TY * TX == NT, "one thread per (y,x) column of the tile");
+constexpr int ST = 4;  // tiles per super-tile edge (rasterisation order, see tile_grid)
 
 struct KView {
   const void* data;
@@ -56,6 +57,8 @@ struct TileView {
   int skip;      // brick does not intersect the view
   int interior;  // every voxel of the tile maps inside [0, n-1]: no per-voxel boundary test
   int wclass;    // WT_*
+  int wdims;     // WT_RAMP: bit d set when axis d leaves the all-ones plateau somewhere in the tile
+  unsigned cpr, total, mc, my;  // staging: 16-byte chunks (or elements) per row, chunk count, magic divisors
 };
 
 // Bounding box, in the index space of an affine map, of the voxels of one tile (fp64), slightly inflated.
@@ -77,18 +80,22 @@ __device__ __forceinline__ void tile_bbox(const double* m, const double* o, int 
 
 // Classify a tile against a view's blending field: every voxel outside the field (weight 0), every voxel
 // on the all-ones plateau (weight 1), fully inside the field (fast float32 path) or touching its rim.
-__device__ __forceinline__ int classify_tile(const KView& kv, int z0, int y0, int x0) {
+__device__ __forceinline__ int classify_tile(const KView& kv, int z0, int y0, int x0, int& wdims) {
+  wdims = 7;
   if (kv.wmode == MVF_W_OFF) return WT_ZERO;
   double lo[3], hi[3];
   tile_bbox(kv.wm, kv.wo, z0, y0, x0, lo, hi);
-  bool zero = false, one = true, ramp = true;
+  bool zero = false, ramp = true;
+  int active = 0;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     zero = zero || (hi[d] < -0.5) || (lo[d] >= (double)MVF_SIG_N - 0.5);
-    one = one && (lo[d] >= (double)kv.one_lo[d]) && (hi[d] < (double)kv.one_hi[d]);
+    const bool plateau = (lo[d] >= (double)kv.one_lo[d]) && (hi[d] < (double)kv.one_hi[d]);
+    active |= plateau ? 0 : (1 << d);
     ramp = ramp && (lo[d] >= 0.0) && (hi[d] < (double)(MVF_SIG_N - 1));
   }
-  return zero ? WT_ZERO : (one ? WT_ONE : (ramp ? WT_RAMP : WT_EDGE));
+  wdims = active;
+  return zero ? WT_ZERO : (active == 0 ? WT_ONE : (ramp ? WT_RAMP : WT_EDGE));
 }
 
 template <int ELEM>
@@ -119,56 +126,96 @@ __device__ __forceinline__ void make_tile_view(const KView& kv, int z0, int y0, 
     t.pz = (t.e[1] * t.px) | 1;
     t.skip = skip;
     t.interior = interior;
+    t.cpr = kv.vec ? t.e[2] / VEC : t.e[2];
+    t.total = t.e[0] * t.e[1] * t.cpr;
+    t.mc = t.cpr > 1 ? 0xFFFFFFFFu / t.cpr + 1u : 0u;
+    t.my = t.e[1] > 1 ? 0xFFFFFFFFu / (unsigned)t.e[1] + 1u : 0u;
   }
-  t.wclass = classify_tile(kv, z0, y0, x0);
+  t.wclass = classify_tile(kv, z0, y0, x0, t.wdims);
 }
 
-struct FastDiv {
-  unsigned m, d;
-  __device__ __forceinline__ explicit FastDiv(unsigned div) : m(div > 1 ? 0xFFFFFFFFu / div + 1u : 0u), d(div) {}
-  __device__ __forceinline__ unsigned div(unsigned x) const { return d > 1 ? __umulhi(x, m) : x; }  // exact for x*d < 2^32
-};
+// blockIdx.x -> tile origin (box-local voxel index); false when the tile lies outside the box
+__device__ __forceinline__ bool tile_origin(const int dims[3], int& z0, int& y0, int& x0) {
+  const unsigned snx = (dims[2] + TX * ST - 1) / (TX * ST), sny = (dims[1] + TY * ST - 1) / (TY * ST);
+  const unsigned b = blockIdx.x;
+  const unsigned inner = b & (ST * ST * ST - 1), sup = b / (ST * ST * ST);
+  const unsigned sx = sup % snx, sy = (sup / snx) % sny, sz = sup / (snx * sny);
+  x0 = (int)((sx * ST + (inner & 3)) * TX);
+  y0 = (int)((sy * ST + ((inner >> 2) & 3)) * TY);
+  z0 = (int)((sz * ST + (inner >> 4)) * TZ);
+  return z0 < dims[0] && y0 < dims[1] && x0 < dims[2];
+}
 
-// Cooperative, coalesced staging of the brick into shared memory as float32; out-of-volume elements are 0.
+#ifndef MVF_PF
+#define MVF_PF 1  // measured on B200 (C2): PF 1/2/4/6 -> 3.84/3.92/4.03/4.22 ms: registers matter more than prefetch depth
+#endif
+constexpr int PF = MVF_PF;  // 16-byte chunks a thread keeps in flight while the previous view is being gathered
+
+// chunk index -> (iz, iy, c) of the brick, exact for index * divisor < 2^32
+__device__ __forceinline__ void chunk_coords(const TileView& t, unsigned i, unsigned& iz, unsigned& iy, unsigned& c) {
+  unsigned row = t.cpr > 1 ? __umulhi(i, t.mc) : i;
+  c = i - row * t.cpr;
+  iz = t.e[1] > 1 ? __umulhi(row, t.my) : row;
+  iy = row - iz * (unsigned)t.e[1];
+}
+
 template <typename T>
-__device__ __forceinline__ void stage_brick(const KView& kv, const TileView& t, float* sm) {
-  const T* __restrict__ src = reinterpret_cast<const T*>(kv.data);
+__device__ __forceinline__ uint4 load_chunk(const KView& kv, const TileView& t, unsigned i) {
   constexpr int VEC = 16 / (int)sizeof(T);
-  const unsigned ey = t.e[1];
-  const FastDiv dy(ey);
-  if (kv.vec) {
-    const unsigned cpr = t.e[2] / VEC;  // 16-byte chunks per brick row
-    const unsigned total = t.e[0] * ey * cpr;
-    const FastDiv dc(cpr);
-    for (unsigned i = threadIdx.x; i < total; i += NT) {
-      unsigned row = dc.div(i);
-      unsigned c = i - row * cpr;
-      unsigned iz = dy.div(row);
-      unsigned iy = row - iz * ey;
-      int gz = t.b0[0] + (int)iz, gy = t.b0[1] + (int)iy, gx = t.b0[2] + (int)c * VEC;
-      float* dst = sm + iz * t.pz + iy * t.px + c * VEC;
-      uint4 q = make_uint4(0u, 0u, 0u, 0u);
-      if ((unsigned)gz < (unsigned)kv.n[0] && (unsigned)gy < (unsigned)kv.n[1] && (unsigned)gx < (unsigned)kv.n[2])
-        q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)gz * kv.n[1] + gy) * kv.n[2] + gx));
-      if (sizeof(T) == 4) {
-        dst[0] = __uint_as_float(q.x); dst[1] = __uint_as_float(q.y);
-        dst[2] = __uint_as_float(q.z); dst[3] = __uint_as_float(q.w);
-      } else {
-        dst[0] = u16_to_float(q.x & 0xFFFFu); dst[1] = u16_to_float(q.x >> 16);
-        dst[2] = u16_to_float(q.y & 0xFFFFu); dst[3] = u16_to_float(q.y >> 16);
-        dst[4] = u16_to_float(q.z & 0xFFFFu); dst[5] = u16_to_float(q.z >> 16);
-        dst[6] = u16_to_float(q.w & 0xFFFFu); dst[7] = u16_to_float(q.w >> 16);
-      }
-    }
+  const T* __restrict__ src = reinterpret_cast<const T*>(kv.data);
+  unsigned iz, iy, c;
+  chunk_coords(t, i, iz, iy, c);
+  int gz = t.b0[0] + (int)iz, gy = t.b0[1] + (int)iy, gx = t.b0[2] + (int)c * VEC;
+  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  if ((unsigned)gz < (unsigned)kv.n[0] && (unsigned)gy < (unsigned)kv.n[1] && (unsigned)gx < (unsigned)kv.n[2])
+    q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)gz * kv.n[1] + gy) * kv.n[2] + gx));
+  return q;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_chunk(const TileView& t, unsigned i, const uint4& q, float* sm) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  unsigned iz, iy, c;
+  chunk_coords(t, i, iz, iy, c);
+  float* dst = sm + iz * t.pz + iy * t.px + c * VEC;
+  if (sizeof(T) == 4) {
+    dst[0] = __uint_as_float(q.x); dst[1] = __uint_as_float(q.y);
+    dst[2] = __uint_as_float(q.z); dst[3] = __uint_as_float(q.w);
   } else {
-    const unsigned ex = t.e[2];
-    const unsigned total = t.e[0] * ey * ex;
-    const FastDiv dx(ex);
-    for (unsigned i = threadIdx.x; i < total; i += NT) {
-      unsigned row = dx.div(i);
-      unsigned ix = i - row * ex;
-      unsigned iz = dy.div(row);
-      unsigned iy = row - iz * ey;
+    dst[0] = u16_to_float(q.x & 0xFFFFu); dst[1] = u16_to_float(q.x >> 16);
+    dst[2] = u16_to_float(q.y & 0xFFFFu); dst[3] = u16_to_float(q.y >> 16);
+    dst[4] = u16_to_float(q.z & 0xFFFFu); dst[5] = u16_to_float(q.z >> 16);
+    dst[6] = u16_to_float(q.w & 0xFFFFu); dst[7] = u16_to_float(q.w >> 16);
+  }
+}
+
+// Issue the loads of the first PF*NT chunks of a brick (vector path); the data stays in registers.
+template <typename T>
+__device__ __forceinline__ void prefetch_brick(const KView& kv, const TileView& t, uint4 (&q)[PF]) {
+#pragma unroll
+  for (int u = 0; u < PF; ++u) {
+    const unsigned i = threadIdx.x + u * NT;
+    q[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (kv.vec && !t.skip && i < t.total) q[u] = load_chunk<T>(kv, t, i);
+  }
+}
+
+// Write a prefetched brick to shared memory as float32 (out-of-volume elements are 0) and fetch whatever
+// did not fit the prefetch registers (very oblique views) or could not be prefetched (unaligned views).
+template <typename T>
+__device__ __forceinline__ void commit_brick(const KView& kv, const TileView& t, const uint4 (&q)[PF], float* sm) {
+  if (kv.vec) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const unsigned i = threadIdx.x + u * NT;
+      if (i < t.total) store_chunk<T>(t, i, q[u], sm);
+    }
+    for (unsigned i = threadIdx.x + PF * NT; i < t.total; i += NT) store_chunk<T>(t, i, load_chunk<T>(kv, t, i), sm);
+  } else {
+    const T* __restrict__ src = reinterpret_cast<const T*>(kv.data);
+    for (unsigned i = threadIdx.x; i < t.total; i += NT) {
+      unsigned iz, iy, ix;
+      chunk_coords(t, i, iz, iy, ix);
       int gz = t.b0[0] + (int)iz, gy = t.b0[1] + (int)iy, gx = t.b0[2] + (int)ix;
       float v = 0.f;
       if ((unsigned)gz < (unsigned)kv.n[0] && (unsigned)gy < (unsigned)kv.n[1] && (unsigned)gx < (unsigned)kv.n[2])
@@ -330,8 +377,23 @@ __device__ __forceinline__ void affine_base(const double* m, const double* o, in
     out[d] = fma(m[d * 3 + 2], (double)x, fma(m[d * 3 + 1], (double)y, fma(m[d * 3 + 0], (double)z, o[d])));
 }
 
+// field value when only axis D leaves the plateau: min(f_D, 1, 1) = f_D, and the trilinear sample collapses
+// to a 1-D lerp (the nested ITK lerps of equal values are exact).
+__device__ __forceinline__ float field_lerp_1d(const float* f, int i, float t) {
+  float a = __ldg(f + i), b = __ldg(f + i + 1);
+  return fmaf(b - a, t, a);
+}
+
+__device__ __forceinline__ void ramp_coord(float cf, float cm, int ci, int k, int& i, float& t) {
+  float c = fmaf((float)k, cm, cf);
+  float y = __fadd_rd(c, MAGIC32);
+  t = c - (y - MAGIC32);
+  i = ci + (__float_as_int(y) - 0x4B400000);
+  i = max(0, min(i, MVF_SIG_N - 2));  // rounding guard at the bbox limits
+}
+
 // Raw (un-normalised) blending weights of the TZ voxels of a thread (fused index (gz+k, gy, gx)) for one view.
-__device__ __forceinline__ void column_blend(const KView& kv, int cls, int gz, int gy, int gx, float (&w)[TZ]) {
+__device__ __forceinline__ void column_blend(const KView& kv, int cls, int wdims, int gz, int gy, int gx, float (&w)[TZ]) {
   if (cls == WT_ZERO || cls == WT_ONE) {
     const float c = cls == WT_ONE ? 1.f : 0.f;
 #pragma unroll
@@ -350,24 +412,60 @@ __device__ __forceinline__ void column_blend(const KView& kv, int cls, int gz, i
       cf[d] = (float)(cb[d] - (double)ci[d]);
       cm[d] = (float)kv.wm[d * 3 + 0];
     }
+    if (wdims == 1 || wdims == 2 || wdims == 4) {  // one active axis (CTA-uniform)
+      const int d = wdims == 1 ? 0 : (wdims == 2 ? 1 : 2);
+      const float* f = kv.prof + d * MVF_SIG_N;
+      const float cfd = cf[d], cmd = cm[d];
+      const int cid = ci[d];
+#pragma unroll
+      for (int k = 0; k < TZ; ++k) {
+        int i;
+        float t;
+        ramp_coord(cfd, cmd, cid, k, i, t);
+        w[k] = field_lerp_1d(f, i, t);
+      }
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < TZ; ++k) {
       int i0[3];
       float t[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        float c = fmaf((float)k, cm[d], cf[d]);
-        float y = __fadd_rd(c, MAGIC32);
-        t[d] = c - (y - MAGIC32);
-        i0[d] = ci[d] + (__float_as_int(y) - 0x4B400000);
-        i0[d] = max(0, min(i0[d], MVF_SIG_N - 2));  // rounding guard at the bbox limits
-      }
+      for (int d = 0; d < 3; ++d) ramp_coord(cf[d], cm[d], ci[d], k, i0[d], t[d]);
       w[k] = field_lerp(kv.prof, i0[0], i0[1], i0[2], i0[0] + 1, i0[1] + 1, i0[2] + 1, t[0], t[1], t[2]);
     }
   } else {
-#pragma unroll 1
-    for (int k = 0; k < TZ; ++k)
-      w[k] = blend_field_exact(kv, fma((double)k, kv.wm[0], cb[0]), fma((double)k, kv.wm[3], cb[1]), fma((double)k, kv.wm[6], cb[2]));
+    // tile touches the rim of the field: the ITK inside test [-0.5, N-0.5) is evaluated exactly in float64, the
+    // sample itself with the float32 index arithmetic above (neighbours clamped to the edge)
+    int ci[3];
+    float cf[3], cm[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ci[d] = __double2int_rd(cb[d]);
+      cf[d] = (float)(cb[d] - (double)ci[d]);
+      cm[d] = (float)kv.wm[d * 3 + 0];
+    }
+#pragma unroll
+    for (int k = 0; k < TZ; ++k) {
+      int i0[3], i1[3];
+      float t[3];
+      bool inside = true;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double c64 = fma((double)k, kv.wm[d * 3 + 0], cb[d]);
+        inside = inside && (c64 >= -0.5) && (c64 < (double)MVF_SIG_N - 0.5);
+        float c = fmaf((float)k, cm[d], cf[d]);
+        float y = __fadd_rd(c, MAGIC32);
+        float tt = c - (y - MAGIC32);
+        int i = ci[d] + (__float_as_int(y) - 0x4B400000);
+        tt = i < 0 ? 0.f : tt;
+        i0[d] = max(0, min(i, MVF_SIG_N - 1));
+        i1[d] = min(i0[d] + 1, MVF_SIG_N - 1);
+        t[d] = tt;
+      }
+      float wv = field_lerp(kv.prof, i0[0], i0[1], i0[2], i1[0], i1[1], i1[2], t[0], t[1], t[2]);
+      w[k] = inside ? wv : 0.f;
+    }
   }
 }
 
@@ -383,7 +481,7 @@ __device__ __forceinline__ void column_weights(const KArgs& A, const TileView* t
   for (int v = 0; v < A.nviews; ++v) {
     const KView& kv = A.v[v];
     float w[TZ];
-    column_blend(kv, tv[v].wclass, gz, gy, gx, w);
+    column_blend(kv, tv[v].wclass, tv[v].wdims, gz, gy, gx, w);
     dct = dct || (kv.wmode == MVF_W_BLEND_DCT);
 #pragma unroll
     for (int k = 0; k < TZ; ++k) {
@@ -416,38 +514,42 @@ __device__ __forceinline__ void column_weights(const KArgs& A, const TileView* t
   }
 }
 
-// Values of one view at the thread's TZ voxels (scipy rule), from the staged brick.
-template <bool INTERIOR>
+// Values of one view at the thread's TZ voxels (scipy rule), from the staged brick; each value is handed to
+// `sink(k, value)` as soon as it is known so that no per-column array of values stays live.
+template <bool INTERIOR, typename Sink>
 __device__ __forceinline__ void column_gather(const float* sm, const TileView& t, const KView& kv, int gz, int gy, int gx,
-                                              float (&val)[TZ]) {
-  double rel[3], step[3], lo[3], hi[3];
+                                              Sink sink) {
+  double rel[3], lo[3], hi[3];
   affine_base(kv.m, kv.o, gz, gy, gx, rel);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     rel[d] -= (double)t.b0[d];
-    step[d] = kv.m[d * 3 + 0];
     lo[d] = -(double)t.b0[d];
     hi[d] = (double)(kv.n[d] - 1 - t.b0[d]);
   }
   const int px = t.px, pz = t.pz;
 #pragma unroll
   for (int k = 0; k < TZ; ++k) {
-    val[k] = gather_scipy<INTERIOR>(sm, px, pz, rel, lo, hi);
+    sink(k, gather_scipy<INTERIOR>(sm, px, pz, rel, lo, hi));
 #pragma unroll
-    for (int d = 0; d < 3; ++d) rel[d] += step[d];
+    for (int d = 0; d < 3; ++d) rel[d] += kv.m[d * 3 + 0];
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: fused single pass
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ KArgs A) {
+#ifndef MVF_MINB
+#define MVF_MINB 3
+#endif
+template <typename T, bool WANT_F32>
+__global__ void __launch_bounds__(NT, MVF_MINB) fuse_blend_kernel(const __grid_constant__ KArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ TileView tv[MVF_MAX_VIEWS];
   float* wsm = reinterpret_cast<float*>(smem_raw);
   float* sm = wsm + A.nviews * TILE_VOX;
-  const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
+  int z0, y0, x0;
+  if (!tile_origin(A.dims, z0, y0, x0)) return;
   const int tid = threadIdx.x;
   if (tid < A.nviews)
     make_tile_view<sizeof(T)>(A.v[tid], z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], true, tv[tid]);
@@ -463,24 +565,31 @@ __global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ 
 #pragma unroll
   for (int k = 0; k < TZ; ++k) { acc[k] = 0u; accf[k] = 0.f; }
 
-  for (int v = 0; v < A.nviews; ++v) {
+  // Software pipeline over the views: the loads of view v+1's brick are in flight (in registers) while view
+  // v is gathered from shared memory.
+  uint4 q[PF];
+  int v = 0;
+  while (v < A.nviews && tv[v].skip) ++v;
+  if (v < A.nviews) prefetch_brick<T>(A.v[v], tv[v], q);
+  while (v < A.nviews) {
     const TileView& t = tv[v];
-    if (t.skip) continue;  // CTA-uniform
     const KView& kv = A.v[v];
+    __syncthreads();  // everybody is done reading the previous brick
+    commit_brick<T>(kv, t, q, sm);
     __syncthreads();
-    stage_brick<T>(kv, t, sm);
-    __syncthreads();
-    float val[TZ];
-    if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, val);
-    else column_gather<false>(sm, t, kv, gz, gy, gx, val);
-#pragma unroll
-    for (int k = 0; k < TZ; ++k) {
-      float wn = __fdiv_rn(wsm[(v * TZ + k) * NT + tid], wsum[k]);
-      float vv = val[k];
+    int vn = v + 1;
+    while (vn < A.nviews && tv[vn].skip) ++vn;
+    if (vn < A.nviews) prefetch_brick<T>(A.v[vn], tv[vn], q);
+    const float* wv = wsm + v * TZ * NT + tid;
+    auto sink = [&](int k, float vv) {
+      float wn = __fdiv_rn(wv[k * NT], wsum[k]);
       if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));  // the transformed view is uint16 (mv:1626)
       acc[k] += trunc_product_u16(wn, vv);
-      accf[k] = fmaf(wn, vv, accf[k]);
-    }
+      if (WANT_F32) accf[k] = fmaf(wn, vv, accf[k]);
+    };
+    if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, sink);
+    else column_gather<false>(sm, t, kv, gz, gy, gx, sink);
+    v = vn;
   }
 
   if (y >= A.dims[1] || x >= A.dims[2]) return;
@@ -491,7 +600,7 @@ __global__ void __launch_bounds__(NT) fuse_blend_kernel(const __grid_constant__ 
     if (z >= A.dims[0]) break;
     const size_t idx = ((size_t)z * A.dims[1] + y) * A.dims[2] + x;
     out[idx] = (uint16_t)(sizeof(T) == 2 ? (acc[k] & 0xFFFFu) : min(acc[k], 65535u));
-    if (A.outf) A.outf[idx] = accf[k];
+    if (WANT_F32) A.outf[idx] = accf[k];
   }
 }
 
@@ -503,7 +612,8 @@ __global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ KA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ TileView tv[1];
   float* sm = reinterpret_cast<float*>(smem_raw);
-  const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
+  int z0, y0, x0;
+  if (!tile_origin(A.dims, z0, y0, x0)) return;
   const int tid = threadIdx.x;
   const KView& kv = A.v[0];
   if (tid == 0) make_tile_view<sizeof(T)>(kv, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], true, tv[0]);
@@ -515,11 +625,14 @@ __global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ KA
 #pragma unroll
   for (int k = 0; k < TZ; ++k) val[k] = 0.f;
   if (!t.skip) {
-    stage_brick<T>(kv, t, sm);
+    uint4 q[PF];
+    prefetch_brick<T>(kv, t, q);
+    commit_brick<T>(kv, t, q, sm);
     __syncthreads();
     if (A.rule == MVF_RULE_SCIPY) {
-      if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, val);
-      else column_gather<false>(sm, t, kv, gz, gy, gx, val);
+      auto sink = [&](int k, float vv) { val[k] = vv; };
+      if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, sink);
+      else column_gather<false>(sm, t, kv, gz, gy, gx, sink);
     } else {
       double rel[3];
       affine_base(kv.m, kv.o, gz, gy, gx, rel);
@@ -552,7 +665,8 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const __grid_constant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ TileView tv[MVF_MAX_VIEWS];
   float* wsm = reinterpret_cast<float*>(smem_raw);
-  const int z0 = blockIdx.z * TZ, y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
+  int z0, y0, x0;
+  if (!tile_origin(A.dims, z0, y0, x0)) return;
   const int tid = threadIdx.x;
   if (tid < A.nviews)
     make_tile_view<4>(A.v[tid], z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], false, tv[tid]);
@@ -661,8 +775,11 @@ static size_t brick_bytes(const KView& k) {
   return ((size_t)k.be[0] * pz + 16) * sizeof(float);
 }
 
+// Tiles are rasterised in 4x4x4 super tiles (32x32x128 voxels) so that tiles sharing brick halos run close
+// together in time and the halo re-reads hit L2 instead of HBM.
 static dim3 tile_grid(const int32_t dims[3]) {
-  return dim3((dims[2] + TX - 1) / TX, (dims[1] + TY - 1) / TY, (dims[0] + TZ - 1) / TZ);
+  unsigned nx = (dims[2] + TX * ST - 1) / (TX * ST), ny = (dims[1] + TY * ST - 1) / (TY * ST), nz = (dims[0] + TZ * ST - 1) / (TZ * ST);
+  return dim3(nx * ny * nz * ST * ST * ST);
 }
 
 static int fill_args(KArgs& A, int nviews, const mvf_view* hv, bool need_data, void* out, float* outf,
@@ -710,8 +827,10 @@ extern "C" int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* 
   int rc = fill_args(A, nviews, host_views, true, out, out_f32, out_dims, out_origin, &brick);
   if (rc) return rc;
   const size_t smem = brick + (size_t)nviews * TILE_VOX * sizeof(float);
-  return host_views[0].dtype == MVF_U16 ? launch_tiles(fuse_blend_kernel<uint16_t>, A, smem, as_stream(stream))
-                                        : launch_tiles(fuse_blend_kernel<float>, A, smem, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (host_views[0].dtype == MVF_U16)
+    return out_f32 ? launch_tiles(fuse_blend_kernel<uint16_t, true>, A, smem, st) : launch_tiles(fuse_blend_kernel<uint16_t, false>, A, smem, st);
+  return out_f32 ? launch_tiles(fuse_blend_kernel<float, true>, A, smem, st) : launch_tiles(fuse_blend_kernel<float, false>, A, smem, st);
 }
 
 extern "C" int mvf_blend_weights(int nviews, const mvf_view* host_views, float* weights_out, const int32_t dims[3],
