@@ -32,6 +32,7 @@ extern "C" {
 #define MVF_ABI_VERSION 1
 #define MVF_MAX_VIEWS 8      /* views fused in one pass (register-resident weights)           */
 #define MVF_SIG_N 200        /* samples per axis of the blending field, mv:3566               */
+#define MVF_RL_KMAX 31       /* longest separable PSF factor handled by the RL kernels         */
 
 enum { MVF_U16 = 0, MVF_F32 = 1 };                 /* voxel dtypes                            */
 enum { MVF_RULE_SCIPY = 0, MVF_RULE_ITK = 1 };     /* boundary rule of order-1 resampling      */
@@ -111,6 +112,45 @@ int mvf_fuse_weighted(int nviews, const void* const* host_view_ptrs, int dtype,
  * out_origin of the fused frame.  out_f32 optional as above. */
 int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* out, float* out_f32,
                    const int32_t out_dims[3], const int32_t out_origin[3], void* stream);
+
+/* ---- K4/K5: multi-view Richardson-Lucy with weights (fuse_LR_with_weights_np, mv:5545-5749) ------
+ * A PSF (get_psf, mv:5376-5418) that is an outer product kz (x) ky (x) kx is passed by its factors
+ * (true-convolution taps, odd sizes).  blur(x)[i] = sum_j psf[j] * ext(i + R - j) with the
+ * reference's boundary handling (reflect above, wrap into the far reflected tail below; closed form
+ * of mv:5654-5673), result clamped at 0.  In y and x the index map is applied inside the kernel; in z
+ * the caller provides `zmap` (device, length dims[0] + 2*Rp, Rp = (mvf_rl_padded_size(max ksize)-1)/2):
+ * zmap[t + Rp] = plane of the input buffer holding extended z position t.  A single-GPU caller fills
+ * it with the same closed form; a z-slab caller points it at halo planes received from its
+ * neighbours, so the kernels are identical in both cases. */
+typedef struct mvf_rl_psf {
+  float kz[MVF_RL_KMAX];
+  float ky[MVF_RL_KMAX];
+  float kx[MVF_RL_KMAX];
+  int32_t ksize[3];
+} mvf_rl_psf;
+
+/* kernel template size used for a PSF whose longest factor has k taps (7, 13, 19, 25 or 31; -1 if k > 31) */
+int mvf_rl_padded_size(int k);
+
+/* estimate = sum_v w_v * I_v (float32, views added in order; mv:5629); *sum_out += sum(estimate). */
+int mvf_rl_init_estimate(int nviews, const void* const* host_view_ptrs, int dtype,
+                         const float* const* host_weight_ptrs, float* est, size_t nvoxels,
+                         double* sum_out, void* stream);
+
+/* out = max(blur(in), 0)                                                          (mv:5654-5673) */
+int mvf_rl_blur(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                float* out, void* stream);
+
+/* ratio_out = I_v / (max(blur(est),0) + 1e-6) * (w_v > 1e-5)                      (mv:5686-5699) */
+int mvf_rl_ratio(const float* est, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                 const void* view, int dtype, const float* weights, float* ratio_out, void* stream);
+
+/* corr (+)= max(blur(ratio),0) * w_v ; on the last view  est = clip(est * corr, 0, 65535) and
+ * *sum_out += sum(est)  (mv:5706-5727).  `est` + est_offset addresses output plane 0 (the estimate
+ * may live in a halo-padded buffer). */
+int mvf_rl_correct(const float* ratio, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                   const float* weights, float* corr, int first, int last, float* est,
+                   int64_t est_offset, double* sum_out, void* stream);
 
 #ifdef __cplusplus
 }

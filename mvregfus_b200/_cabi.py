@@ -19,7 +19,9 @@ MVF_W_OFF, MVF_W_BLEND, MVF_W_BLEND_DCT = 0, 1, 2
 EXPORTS = (
     "mvf_abi_version", "mvf_last_error", "mvf_launch_count",
     "mvf_affine_resample", "mvf_blend_weights", "mvf_fuse_weighted", "mvf_fuse_blend",
+    "mvf_rl_padded_size", "mvf_rl_init_estimate", "mvf_rl_blur", "mvf_rl_ratio", "mvf_rl_correct",
 )
+MVF_RL_KMAX = 31
 
 
 class MvfView(C.Structure):
@@ -43,6 +45,11 @@ class MvfView(C.Structure):
     ]
 
 
+class MvfRlPsf(C.Structure):
+    """struct mvf_rl_psf: separable PSF factors (true-convolution taps)."""
+    _fields_ = [("kz", C.c_float * 31), ("ky", C.c_float * 31), ("kx", C.c_float * 31), ("ksize", C.c_int32 * 3)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -63,9 +70,17 @@ def _declare(lib):
     lib.mvf_fuse_weighted.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]
     lib.mvf_fuse_blend.argtypes = [C.c_int, C.POINTER(MvfView), C.c_void_p, C.c_void_p, i32p, i32p, C.c_void_p]
+    psfp = C.POINTER(MvfRlPsf)
+    lib.mvf_rl_padded_size.argtypes = [C.c_int]
+    lib.mvf_rl_init_estimate.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
+                                         C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_blur.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_ratio.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_correct.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version"):
+        if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version", "mvf_rl_padded_size"):
             fn.restype = C.c_int
 
 

@@ -1,0 +1,307 @@
+// K4/K5: multi-view Richardson-Lucy deconvolution (reference: mvregfus/multiview.py:5545-5749,
+// fuse_LR_with_weights_np) for separable PSFs, sm_100a.
+//
+// One kernel computes a full 3-D blur-in-view  out[i] = sum_j psf[j] * ext(i + R - j)  (the closed form of the
+// reference's reflect-padded circular FFT convolution) as three 1-D passes without any
+// intermediate volume in HBM: a CTA owns a 32x32 (y,x) column of the volume and streams along z; per input
+// plane the x pass and the y pass run through shared memory with 4-wide register windows, and the z pass is a
+// K-deep shift register of partial sums held in registers (4 columns x K accumulators per thread).  The RL
+// pointwise algebra is fused into the epilogue:
+//   ratio  : R_v = I_v / (max(blur(est),0) + 1e-6) * (w_v > 1e-5)                         (mv:5686-5699)
+//   correct: C (+)= max(blur(R_v),0) * w_v ; last view: est = clip(est * C, 0, 65535)      (mv:5706-5723)
+// so one blur moves 4 B in + its epilogue operands instead of three read+write passes.  The same PSF is used
+// un-flipped for the "transpose" (mv:5710).  Boundary handling in y/x is the closed-form index map; in z it is a
+// caller-provided plane map so that a z-slab with NCCL-exchanged halo planes uses the very same kernel.
+#include "common.cuh"
+
+namespace mvf {
+
+constexpr int RL_TX = 32, RL_TY = 32, RL_NT = 256, RL_CPT = 4;  // 4 (y) columns per thread
+constexpr int RL_KMAX = MVF_RL_KMAX;
+
+enum { RL_PLAIN = 0, RL_RATIO = 1, RL_CORRECT = 2 };
+
+struct RLArgs {
+  const float* in;      // input buffer (planes of ny*nx floats)
+  const int* zmap;      // extended z position (t + Rz) -> plane of `in`; length nz + 2*Rz
+  float kz[RL_KMAX], ky[RL_KMAX], kx[RL_KMAX];  // taps, zero padded (centred) to the template size
+  int ksz_y, ksz_x;     // ORIGINAL kernel sizes in y/x (the wrap quirk of the index map depends on them)
+  int nz, ny, nx;       // output extents
+  int zchunk;           // output planes per CTA
+  // epilogue operands
+  const void* view;     // RATIO: I_v (uint16 or float32)
+  int view_u16;
+  const float* weights; // RATIO: mask = w > 1e-5 ; CORRECT: multiplier
+  float* out;           // PLAIN: blur ; RATIO: R_v ; CORRECT: correction factor C
+  int first, last;      // CORRECT: first view initialises C, last view applies the update
+  float* est;           // CORRECT+last: estimate planes (may live in a halo-padded buffer)
+  long long est_off;    // element offset of output plane 0 inside `est`
+  double* sum;          // CORRECT+last: sum(est) accumulated here (convergence test, mv:5726)
+};
+
+// index map of the reference's boundary handling: reflect (no edge repeat) above, wrap into
+// the far reflected tail below.  Clamped so that positions never used by a valid output stay in range.
+__device__ __forceinline__ int ext_index(int t, int n, int K) {
+  int i = t < 0 ? n - 3 - K - t : (t >= n ? 2 * n - 2 - t : t);
+  return max(0, min(i, n - 1));
+}
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant__ RLArgs A) {
+  constexpr int R = (K - 1) / 2;
+  constexpr int AY = RL_TY + 2 * R, AX = RL_TX + 2 * R;
+  constexpr int PA = AX | 1;       // odd pitch: the strided x-pass windows are conflict free
+  constexpr int PB = RL_TX + 1;
+  __shared__ float sA[AY * PA];
+  __shared__ float sB[AY * PB];
+  __shared__ int sRowOff[AY];      // ext-mapped source row offsets (y * nx)
+  __shared__ int sCol[AX];         // ext-mapped source columns
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * RL_TX, y0 = blockIdx.y * RL_TY;
+  const int zo0 = blockIdx.z * A.zchunk, zo1 = min(A.nz, zo0 + A.zchunk);
+  if (tid < AY) sRowOff[tid] = ext_index(y0 - R + tid, A.ny, A.ksz_y) * A.nx;
+  if (tid >= 64 && tid < 64 + AX) sCol[tid - 64] = ext_index(x0 - R + (tid - 64), A.nx, A.ksz_x);
+
+  float S[RL_CPT][K];
+#pragma unroll
+  for (int c = 0; c < RL_CPT; ++c)
+#pragma unroll
+    for (int j = 0; j < K; ++j) S[c][j] = 0.f;
+
+  const int x = x0 + lane;
+  const size_t plane = (size_t)A.ny * A.nx;
+  double local_sum = 0.0;
+  __syncthreads();
+
+  for (int t = zo0 - R; t < zo1 + R; ++t) {
+    const float* __restrict__ src = A.in + (size_t)A.zmap[t + R] * plane;
+    // ---- load the (AY x AX) input tile of this plane
+    for (int i = tid; i < AY * AX; i += RL_NT) {
+      int r = i / AX, c = i - r * AX;
+      sA[r * PA + c] = __ldg(src + sRowOff[r] + sCol[c]);
+    }
+    __syncthreads();
+    // ---- x pass: strips of 4 outputs, 4 + 2R loaded values each
+    for (int item = tid; item < AY * (RL_TX / 4); item += RL_NT) {
+      const int r = item >> 3, s = item & 7;
+      const float* a = sA + r * PA + s * 4;
+      float win[4 + 2 * R];
+#pragma unroll
+      for (int j = 0; j < 4 + 2 * R; ++j) win[j] = a[j];
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {  // out[x] = sum_j k[j] * in[x + 2R - j]  (tile-local columns)
+        const float kj = A.kx[j];
+        o0 = fmaf(kj, win[0 + 2 * R - j], o0);
+        o1 = fmaf(kj, win[1 + 2 * R - j], o1);
+        o2 = fmaf(kj, win[2 + 2 * R - j], o2);
+        o3 = fmaf(kj, win[3 + 2 * R - j], o3);
+      }
+      float* b = sB + r * PB + s * 4;
+      b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3;
+    }
+    __syncthreads();
+    // ---- y pass: thread (lane = x, warp = strip of 4 y), then the z shift register
+    {
+      const float* b = sB + (warp * 4) * PB + lane;
+      float win[4 + 2 * R];
+#pragma unroll
+      for (int j = 0; j < 4 + 2 * R; ++j) win[j] = b[j * PB];
+      float p[RL_CPT] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float kj = A.ky[j];
+#pragma unroll
+        for (int c = 0; c < RL_CPT; ++c) p[c] = fmaf(kj, win[c + 2 * R - j], p[c]);
+      }
+      const int z = t - R;  // the output plane completed by this input plane
+      const bool emit = z >= zo0;
+#pragma unroll
+      for (int c = 0; c < RL_CPT; ++c) {
+        const float e = fmaf(A.kz[0], p[c], S[c][0]);
+#pragma unroll
+        for (int m = 0; m < K - 1; ++m) S[c][m] = fmaf(A.kz[m + 1], p[c], S[c][m + 1]);
+        S[c][K - 1] = 0.f;
+        const int y = y0 + warp * 4 + c;
+        if (emit && y < A.ny && x < A.nx) {
+          const size_t idx = (size_t)z * plane + (size_t)y * A.nx + x;
+          const float blur = fmaxf(e, 0.f);  // img_ft[img_ft<0] = 0 (mv:5671)
+          if (MODE == RL_PLAIN) {
+            A.out[idx] = blur;
+          } else if (MODE == RL_RATIO) {
+            const float I = A.view_u16 ? u16_to_float(reinterpret_cast<const uint16_t*>(A.view)[idx])
+                                       : reinterpret_cast<const float*>(A.view)[idx];
+            const float w = A.weights[idx];
+            const float ratio = __fdiv_rn(I, blur + 1e-6f);
+            A.out[idx] = w > 1e-5f ? ratio : 0.f;
+          } else {
+            const float o = blur * A.weights[idx];
+            const float corr = A.first ? o : A.out[idx] + o;
+            if (A.last) {
+              float* ep = A.est + A.est_off + idx;
+              const float v = fminf(fmaxf(*ep * corr, 0.f), 65535.f);
+              *ep = v;
+              local_sum += (double)v;
+            } else {
+              A.out[idx] = corr;
+            }
+          }
+        }
+      }
+    }
+    // sA/sB are rewritten only after the next barrier pair; the y pass reads sB, the next load writes sA
+  }
+  if (MODE == RL_CORRECT && A.last && A.sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_sum += __shfl_xor_sync(0xffffffffu, local_sum, o);
+    if (lane == 0) atomicAdd(A.sum, local_sum);
+  }
+}
+
+// estimate = sum_v w_v * I_v in float32, views added in order (np.sum(weights * data, 0), mv:5629)
+struct RLInitArgs {
+  const void* views[MVF_MAX_VIEWS];
+  const float* weights[MVF_MAX_VIEWS];
+  float* est;
+  double* sum;
+  size_t n;
+  int nviews, u16;
+};
+
+__global__ void __launch_bounds__(256) rl_init_kernel(const __grid_constant__ RLInitArgs A) {
+  double local = 0.0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < A.n; i += (size_t)gridDim.x * 256) {
+    float s = 0.f;
+    for (int v = 0; v < A.nviews; ++v) {
+      const float I = A.u16 ? u16_to_float(reinterpret_cast<const uint16_t*>(A.views[v])[i])
+                            : reinterpret_cast<const float*>(A.views[v])[i];
+      const float p = __fmul_rn(A.weights[v][i], I);
+      s = v == 0 ? p : __fadd_rn(s, p);
+    }
+    A.est[i] = s;
+    local += (double)s;
+  }
+  if (A.sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(A.sum, local);
+  }
+}
+
+static int padded_size(int k) {
+  const int sizes[] = {7, 13, 19, 25, 31};
+  for (int s : sizes)
+    if (k <= s) return s;
+  return -1;
+}
+
+template <int MODE>
+static int launch_rl(int kp, const RLArgs& A, cudaStream_t st) {
+  dim3 grid((A.nx + RL_TX - 1) / RL_TX, (A.ny + RL_TY - 1) / RL_TY, (A.nz + A.zchunk - 1) / A.zchunk);
+  switch (kp) {
+    case 7: rl_blur_kernel<7, MODE><<<grid, RL_NT, 0, st>>>(A); break;
+    case 13: rl_blur_kernel<13, MODE><<<grid, RL_NT, 0, st>>>(A); break;
+    case 19: rl_blur_kernel<19, MODE><<<grid, RL_NT, 0, st>>>(A); break;
+    case 25: rl_blur_kernel<25, MODE><<<grid, RL_NT, 0, st>>>(A); break;
+    case 31: rl_blur_kernel<31, MODE><<<grid, RL_NT, 0, st>>>(A); break;
+    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 31 taps");
+  }
+  MVF_LAUNCHED();
+  return MVF_OK;
+}
+
+static int fill_rl(RLArgs& A, const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf, int* kp) {
+  memset(&A, 0, sizeof(A));
+  if (!in || !zmap || !dims || !psf) return fail(MVF_ERR_INVALID, "%s%s", "rl: NULL argument");
+  int kmax = 0;
+  for (int d = 0; d < 3; ++d) {
+    if (psf->ksize[d] < 1 || psf->ksize[d] > RL_KMAX || !(psf->ksize[d] & 1))
+      return fail(MVF_ERR_INVALID, "%s%s", "rl: PSF sizes must be odd and <= 31");
+    if (dims[d] < psf->ksize[d] + 3)
+      return fail(MVF_ERR_UNSUPPORTED, "%s%s", "rl: volume extent smaller than PSF size + 3 (the reference's reflect padding needs it)");
+    kmax = psf->ksize[d] > kmax ? psf->ksize[d] : kmax;
+  }
+  *kp = padded_size(kmax);
+  if (*kp < 0) return fail(MVF_ERR_UNSUPPORTED, "%s%s", "rl: PSF too large");
+  const float* taps[3] = {psf->kz, psf->ky, psf->kx};
+  float* dst[3] = {A.kz, A.ky, A.kx};
+  for (int d = 0; d < 3; ++d) {
+    const int pad = (*kp - psf->ksize[d]) / 2;
+    for (int j = 0; j < psf->ksize[d]; ++j) dst[d][pad + j] = taps[d][j];
+  }
+  A.in = in; A.zmap = zmap;
+  A.ksz_y = psf->ksize[1]; A.ksz_x = psf->ksize[2];
+  A.nz = dims[0]; A.ny = dims[1]; A.nx = dims[2];
+  // z chunk: enough CTAs to fill the GPU twice, at least 32 planes so the 2R-plane ramp-up stays small
+  const int cols = ((A.nx + RL_TX - 1) / RL_TX) * ((A.ny + RL_TY - 1) / RL_TY);
+  int chunks = (2 * 2 * sm_count() + cols - 1) / cols;
+  int zc = (A.nz + chunks - 1) / chunks;
+  if (zc < 32) zc = 32;
+  if (zc > A.nz) zc = A.nz;
+  A.zchunk = zc;
+  return MVF_OK;
+}
+
+}  // namespace mvf
+
+using namespace mvf;
+
+extern "C" int mvf_rl_padded_size(int k) { return padded_size(k); }
+
+extern "C" int mvf_rl_blur(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                           float* out, void* stream) {
+  RLArgs A;
+  int kp;
+  int rc = fill_rl(A, in, zmap, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(out, "NULL out");
+  A.out = out;
+  return launch_rl<RL_PLAIN>(kp, A, as_stream(stream));
+}
+
+extern "C" int mvf_rl_ratio(const float* est, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                            const void* view, int dtype, const float* weights, float* ratio_out, void* stream) {
+  RLArgs A;
+  int kp;
+  int rc = fill_rl(A, est, zmap, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(view && weights && ratio_out, "NULL argument");
+  MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
+  A.view = view; A.view_u16 = dtype == MVF_U16; A.weights = weights; A.out = ratio_out;
+  return launch_rl<RL_RATIO>(kp, A, as_stream(stream));
+}
+
+extern "C" int mvf_rl_correct(const float* ratio, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                              const float* weights, float* corr, int first, int last, float* est,
+                              int64_t est_offset, double* sum_out, void* stream) {
+  RLArgs A;
+  int kp;
+  int rc = fill_rl(A, ratio, zmap, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(weights && corr, "NULL argument");
+  MVF_CHECK_ARG(!last || est, "est must be given for the last view");
+  A.weights = weights; A.out = corr; A.first = first; A.last = last; A.est = est; A.est_off = est_offset; A.sum = sum_out;
+  return launch_rl<RL_CORRECT>(kp, A, as_stream(stream));
+}
+
+extern "C" int mvf_rl_init_estimate(int nviews, const void* const* host_view_ptrs, int dtype,
+                                    const float* const* host_weight_ptrs, float* est, size_t nvoxels,
+                                    double* sum_out, void* stream) {
+  MVF_CHECK_ARG(nviews >= 1 && nviews <= MVF_MAX_VIEWS, "nviews must be in [1, MVF_MAX_VIEWS]");
+  MVF_CHECK_ARG(host_view_ptrs && host_weight_ptrs && est, "NULL argument");
+  MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
+  RLInitArgs A;
+  memset(&A, 0, sizeof(A));
+  for (int v = 0; v < nviews; ++v) {
+    MVF_CHECK_ARG(host_view_ptrs[v] && host_weight_ptrs[v], "NULL view/weight pointer");
+    A.views[v] = host_view_ptrs[v];
+    A.weights[v] = host_weight_ptrs[v];
+  }
+  A.est = est; A.sum = sum_out; A.n = nvoxels; A.nviews = nviews; A.u16 = dtype == MVF_U16;
+  if (nvoxels == 0) return MVF_OK;
+  size_t blocks = (nvoxels + 255) / 256, cap = (size_t)sm_count() * 16;
+  rl_init_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(A);
+  MVF_LAUNCHED();
+  return MVF_OK;
+}

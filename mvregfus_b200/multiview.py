@@ -19,6 +19,7 @@ __all__ = [
     "transform_stack_sitk", "transform_stack_dask_numpy", "affine_transform_dask",
     "get_weights_simple", "blocks_inside", "fuse_views_weights", "get_sample_volume", "get_union_volume",
     "calc_stack_properties_from_volume", "calc_stack_properties_from_views_and_params",
+    "get_psf", "fuse_LR_with_weights_np",
 ]
 
 
@@ -170,3 +171,41 @@ def fuse_views_weights(views, params, stack_properties, weights=None, views_in_t
             raise Exception("fuse_views_weights: more than 8 views are not supported by one fused pass")
         out = fusion.fuse_weighted(dviews[i0:i0 + 8], dweights[i0:i0 + 8] if dweights is not None else None)
     return ImageArray(out.cpu().numpy(), spacing=stack_properties["spacing"], origin=stack_properties["origin"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# a14/a15: PSF and multi-view Richardson-Lucy
+# ---------------------------------------------------------------------------------------------------
+def get_psf(p, stack_properties, sz, sxy):
+    """Gaussian PSF of a view in the fused frame (mv:5376-5418): a delta filtered with sigma (sz, sxy, sxy),
+    rotated by the view's affine (translation dropped) with ITK-linear resampling, normalised, float32.
+    Host arithmetic (a (3*max sigma)^3 array) except for the rotation, which runs through K1."""
+    from scipy import ndimage
+    spacing = np.asarray(stack_properties['spacing'], dtype=np.float64)
+    psf_shape = (np.array([np.max([1, np.max([sz, sxy, sxy]) * 3])]) / spacing).astype(np.int64)
+    psf_shape = np.array([ps + [1, 0][int(ps % 2)] for ps in psf_shape]).astype(np.int64)  # odd
+    psf_orig = np.zeros(psf_shape, dtype=np.float32)
+    psf_orig[psf_shape[0] // 2, psf_shape[1] // 2, psf_shape[2] // 2] = 1
+    psf_orig = ndimage.gaussian_filter(psf_orig, np.array([sz, sxy, sxy]) / spacing)
+    origin = -spacing * (psf_shape // 2)
+    psf_orig = ImageArray(psf_orig, spacing=spacing, origin=origin)
+    tmpp = np.copy(np.asarray(p, dtype=np.float64))
+    tmpp[-3:] = 0
+    psf_target = transform_stack_sitk(psf_orig, tmpp, out_origin=origin, out_shape=psf_shape, out_spacing=spacing,
+                                      interp='linear')
+    psf_target = np.asarray(psf_target)
+    psf_target = psf_target / np.sum(psf_target)
+    return psf_target.astype(np.float32)
+
+
+def fuse_LR_with_weights_np(views, params, stack_properties, num_iterations=25, sz=4, sxy=0.5, tol=5e-5,
+                            weights=None):
+    """Multi-view Richardson-Lucy with weights (mv:5545-5749): returns the uint16 ImageArray estimate."""
+    from . import rl
+    psfs = [get_psf(params[ip], stack_properties, sz, sxy) for ip in range(len(params))]
+    dviews = [fusion.to_device(v) for v in views]
+    dweights = [fusion.to_device(np.asarray(w, dtype=np.float32)) for w in weights]
+    plan = rl.RLPlan(dviews, dweights, psfs)
+    est = plan.run(num_iterations=num_iterations, tol=tol)
+    est = est.cpu().numpy()
+    return ImageArray(est.astype(np.uint16), spacing=stack_properties['spacing'], origin=stack_properties['origin'])

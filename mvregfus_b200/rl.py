@@ -1,0 +1,142 @@
+"""Multi-view Richardson-Lucy deconvolution on device tensors (reference: mvregfus/multiview.py:5545-5749).
+
+Host side: PSF construction helpers (separability test), the z plane maps that encode the reference's boundary
+handling, and the iteration loop.  The blurs and the fused pointwise algebra run in csrc/rl.cu.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .fusion import _stream_ptr, dtype_code
+
+
+def factor_psf(psf, tol=2e-6):
+    """(kz, ky, kx) with psf ~= kz (x) ky (x) kx, or None if the PSF is not separable to float32 accuracy.
+
+    The PSF of an axis-aligned view (get_psf, mv:5376-5418) is a Gaussian filtered delta, i.e. an outer product;
+    its factors are recovered from the marginals."""
+    p = np.asarray(psf, dtype=np.float64)
+    total = p.sum()
+    if not np.isfinite(total) or total == 0:
+        return None
+    kz, ky, kx = p.sum((1, 2)), p.sum((0, 2)), p.sum((0, 1))
+    approx = kz[:, None, None] * ky[None, :, None] * kx[None, None, :] / total ** 2
+    if np.max(np.abs(approx - p)) > tol * np.max(np.abs(p)):
+        return None
+    return (kz / total).astype(np.float32), (ky / total).astype(np.float32), kx.astype(np.float32)
+
+
+def make_psf_struct(factors):
+    s = _cabi.MvfRlPsf()
+    for name, k in zip(("kz", "ky", "kx"), factors):
+        if len(k) > _cabi.MVF_RL_KMAX or len(k) % 2 == 0:
+            raise ValueError("PSF factors must have odd length <= %d" % _cabi.MVF_RL_KMAX)
+        arr = getattr(s, name)
+        for j, val in enumerate(k):
+            arr[j] = float(val)
+    s.ksize = _cabi.i32x3([len(k) for k in factors])
+    return s
+
+
+def padded_radius(factors):
+    kp = _cabi.load().mvf_rl_padded_size(int(max(len(k) for k in factors)))
+    if kp < 0:
+        raise ValueError("PSF longer than %d taps" % _cabi.MVF_RL_KMAX)
+    return (kp - 1) // 2
+
+
+def ext_index(t, n, K):
+    """Index map of the reference's FFT convolution: reflect above, wrap into the far reflected
+    tail below; clamped for positions no valid output uses."""
+    t = np.asarray(t)
+    i = np.where(t < 0, n - 3 - K - t, np.where(t >= n, 2 * n - 2 - t, t))
+    return np.clip(i, 0, n - 1)
+
+
+def zmap_whole(nz, kz_size, rp):
+    """Plane map of a whole (unsharded) volume: extended position t in [-rp, nz+rp) -> plane."""
+    return ext_index(np.arange(-rp, nz + rp), nz, kz_size).astype(np.int32)
+
+
+class RLPlan:
+    """Device buffers and PSF structs of one multi-view RL problem on one GPU (whole volume)."""
+
+    def __init__(self, views, weights, psfs):
+        self.lib = _cabi.load()
+        self.views, self.weights = views, weights
+        self.n = len(views)
+        self.dims = tuple(int(s) for s in views[0].shape)
+        dev = views[0].device
+        self.factors = []
+        for p in psfs:
+            f = factor_psf(p)
+            if f is None:
+                raise NotImplementedError(
+                    "non-separable PSF (view not axis aligned): the FFT path is not built yet in this round")
+            self.factors.append(f)
+        self.psf_structs = [make_psf_struct(f) for f in self.factors]
+        self.zmaps = [torch.from_numpy(zmap_whole(self.dims[0], len(f[0]), padded_radius(f))).to(dev) for f in self.factors]
+        self.est = torch.empty(self.dims, dtype=torch.float32, device=dev)
+        self.ratio = torch.empty(self.dims, dtype=torch.float32, device=dev)
+        self.corr = torch.empty(self.dims, dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(2, dtype=torch.float64, device=dev)
+        self._vp = (C.c_void_p * self.n)(*[v.data_ptr() for v in views])
+        self._wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in weights])
+        self._dims = _cabi.i32x3(self.dims)
+
+    def init_estimate(self):
+        self.sums.zero_()
+        _cabi.check(self.lib.mvf_rl_init_estimate(self.n, self._vp, dtype_code(self.views[0]), self._wp,
+                                                  C.c_void_p(self.est.data_ptr()), self.est.numel(),
+                                                  C.c_void_p(self.sums.data_ptr()), _stream_ptr()))
+
+    def iterate(self):
+        """One RL iteration (2 V fused blur kernels); sum(estimate) lands in self.sums[1]."""
+        st = _stream_ptr()
+        self.sums[1:].zero_()
+        for v in range(self.n):
+            zm = C.c_void_p(self.zmaps[v].data_ptr())
+            _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est.data_ptr()), zm, self._dims, C.byref(self.psf_structs[v]),
+                                              C.c_void_p(self.views[v].data_ptr()), dtype_code(self.views[v]),
+                                              C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.ratio.data_ptr()), st))
+            last = v == self.n - 1
+            _cabi.check(self.lib.mvf_rl_correct(C.c_void_p(self.ratio.data_ptr()), zm, self._dims, C.byref(self.psf_structs[v]),
+                                                C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.corr.data_ptr()),
+                                                1 if v == 0 else 0, 1 if last else 0, C.c_void_p(self.est.data_ptr()), 0,
+                                                C.c_void_p(self.sums[1:].data_ptr()), st))
+
+    def run(self, num_iterations=25, tol=5e-5):
+        """The reference's loop (mv:5678-5734): stops after num_iterations, or once i >= 10 and the relative
+        change of sum(estimate) drops below tol."""
+        self.init_estimate()
+        curr = None
+        i = 0
+        while True:
+            self.iterate()
+            if i >= 10:  # the convergence test can only fire from the 11th iteration on: no sync before that
+                s = self.sums.cpu().numpy()
+                curr = s[0] if curr is None else curr
+                new = s[1]
+                if abs(1 - new / curr) < tol:
+                    break
+                curr = new
+            else:
+                self.sums[0] = self.sums[1]
+            if i >= num_iterations - 1:
+                break
+            i += 1
+        return self.est
+
+
+def blur(volume, psf_factors):
+    """max(blur(volume), 0) of a float32 CUDA tensor with a separable PSF (tests, PSF checks)."""
+    lib = _cabi.load()
+    dims = tuple(int(s) for s in volume.shape)
+    zm = torch.from_numpy(zmap_whole(dims[0], len(psf_factors[0]), padded_radius(psf_factors))).to(volume.device)
+    out = torch.empty_like(volume)
+    ps = make_psf_struct(psf_factors)
+    _cabi.check(lib.mvf_rl_blur(C.c_void_p(volume.data_ptr()), C.c_void_p(zm.data_ptr()), _cabi.i32x3(dims), C.byref(ps),
+                                C.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
