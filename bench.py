@@ -119,6 +119,68 @@ def make_workload(device, seed, dtype="f32"):
     return views, params, props, sp
 
 
+RL_SHAPE = (512, 1024, 1024)
+RL_SIGMA = (6.0, 2.0)  # sz, sxy  -> 19^3 PSF at spacing 1 (BASELINE.json configs[3])
+RL_ITERS = 10
+
+
+def run_rl(dev, steps_cap=1):
+    """BASELINE.json configs[3]: 4 views 1024x1024x512 uint16, Gaussian PSF sigma 2x2x6, 10 RL iterations, on the
+    transformed views and blending weights produced by the fusion kernels.  Returns the `rl` JSON object."""
+    import torch
+    import torch.nn.functional as F
+    from mvregfus_b200 import fusion, rl, synthetic
+    from mvregfus_b200 import multiview as mv
+    shape = RL_SHAPE
+    g = torch.Generator(device=dev)
+    g.manual_seed(4004)
+    fine = torch.rand((1, 1) + tuple(s // 16 for s in shape), generator=g, device=dev)
+    gt = F.interpolate(fine, size=shape, mode="trilinear", align_corners=True)[0, 0]
+    ax = [torch.linspace(-1, 1, s, device=dev) for s in shape]
+    r2 = (ax[0][:, None, None] / 0.9) ** 2 + (ax[1][None, :, None] / 0.9) ** 2 + (ax[2][None, None, :] / 0.9) ** 2
+    gt = (gt * 3000.0 * (r2 <= 1.0)).contiguous()
+    del fine, r2
+    params = synthetic.view_params(shape, NVIEWS, seed=4004)
+    props = [{"size": np.array(shape), "spacing": np.ones(3), "origin": np.zeros(3)} for _ in range(NVIEWS)]
+    sp = {"size": np.array(shape), "spacing": np.ones(3), "origin": np.zeros(3)}
+    tviews = []
+    for v in range(NVIEWS):
+        A, c = params[v][:9].reshape(3, 3), params[v][9:]
+        Ainv = np.linalg.inv(A)
+        view = fusion.affine_resample(gt, Ainv, -Ainv @ c, shape, rule="scipy")          # the raw view
+        view = view.clamp_(0, 4095).round_().to(torch.int32).to(torch.uint16)
+        M, off = mv.index_space_affine(params[v], props[v]["spacing"], props[v]["origin"], sp["spacing"], sp["origin"])
+        tviews.append(fusion.affine_resample(view, M, off, shape, rule="scipy"))             # transformed view
+        del view
+    del gt
+    vs = fusion.build_viewset(None, props, params, sp, weights="blending")
+    w = fusion.blend_weights(vs, shape, normalise=True)
+    psfs = [mv.get_psf(params[v], sp, RL_SIGMA[0], RL_SIGMA[1]) for v in range(NVIEWS)]
+    plan = rl.RLPlan(tviews, [w[v] for v in range(NVIEWS)], psfs)
+    plan.init_estimate()
+    plan.iterate()  # warm-up
+    torch.cuda.synchronize()
+    plan.init_estimate()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(RL_ITERS):
+        plan.iterate()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    nvox = int(np.prod(shape))
+    peak, how = measured_peak_gbs()
+    alg = (12 + NVIEWS * (16 + 2)) * nvox
+    per_it = ms / RL_ITERS
+    return {"metric": "rl_iterations_per_s", "value": 1e3 / per_it, "unit": "it/s", "ms_per_iteration": per_it,
+            "config": {"workload": "BASELINE.json configs[3]: %d views %dx%dx%d uint16 in the fused frame, Gaussian PSF "
+                                   "sigma z=%g xy=%g (19^3, separable), %d iterations" % (NVIEWS, *shape, *RL_SIGMA, RL_ITERS)},
+            "kernel_launches_per_iteration": 2 * NVIEWS,
+            "roofline": {"bound": "hbm", "achieved": alg / (per_it * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (per_it * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_iteration": alg,
+                         "peak_source": how}}
+
+
 def cpu_baseline(views_host, params, props, sp, box=96, threads=1):
     """Oracle (= the reference's numpy/scipy arithmetic) on a centred sub-box of the same workload,
     chunked like the reference's transform_chunk / fuse_block.  Returns (Gvoxel/s, seconds, description)."""
@@ -290,6 +352,10 @@ def run_b200(args):
                              "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                              "kernel": "fuse_blend_kernel<float,4>", "kernel_ms": kernel_ms,
                              "algorithmic_bytes": alg_bytes}}
+        if not args.skip_rl and world == 1:
+            del views, dviews, vs, vs2, out
+            torch.cuda.empty_cache()
+            line["rl"] = run_rl(dev)
         if not args.no_cpu_baseline:
             views_host = [p.numpy() for p in pinned]
             gv, dt, sample = cpu_baseline(views_host, params, props, sp, box=96, threads=1)
@@ -307,6 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-rl", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -46,22 +46,44 @@ __device__ __forceinline__ int ext_index(int t, int n, int K) {
   return max(0, min(i, n - 1));
 }
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 template <int K, int MODE>
 __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant__ RLArgs A) {
   constexpr int R = (K - 1) / 2;
-  constexpr int AY = RL_TY + 2 * R, AX = RL_TX + 2 * R;
-  constexpr int PA = AX | 1;       // odd pitch: the strided x-pass windows are conflict free
+  constexpr int LEAD = (R + 3) & ~3;            // x halo rounded up to whole 16-byte chunks
+  constexpr int AY = RL_TY + 2 * R, AX = RL_TX + 2 * LEAD;
+  constexpr int PA = AX;                        // multiple of 4: rows are 16-byte aligned for cp.async / LDS.128
   constexpr int PB = RL_TX + 1;
-  __shared__ float sA[AY * PA];
+  constexpr int CPR = AX / 4;                   // 16-byte chunks per tile row
+  constexpr int NV = (AY * CPR + RL_NT - 1) / RL_NT;   // vector copies per thread and plane
+  constexpr int NS = (AY * AX + RL_NT - 1) / RL_NT;    // scalar copies (tiles touching the x border / unaligned rows)
+  constexpr int WIN = 4 + 2 * LEAD;             // x-pass register window (whole chunks)
+  __shared__ __align__(16) float sA[2][AY * PA];  // double buffered: plane t+1 streams in while plane t is filtered
   __shared__ float sB[AY * PB];
   __shared__ int sRowOff[AY];      // ext-mapped source row offsets (y * nx)
   __shared__ int sCol[AX];         // ext-mapped source columns
+  extern __shared__ int sZ[];      // plane map of this CTA's z range
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.x * RL_TX, y0 = blockIdx.y * RL_TY;
   const int zo0 = blockIdx.z * A.zchunk, zo1 = min(A.nz, zo0 + A.zchunk);
+  const int t_begin = zo0 - R, t_end = zo1 + R;
   if (tid < AY) sRowOff[tid] = ext_index(y0 - R + tid, A.ny, A.ksz_y) * A.nx;
-  if (tid >= 64 && tid < 64 + AX) sCol[tid - 64] = ext_index(x0 - R + (tid - 64), A.nx, A.ksz_x);
+  if (tid >= 64 && tid < 64 + AX) sCol[tid - 64] = ext_index(x0 - LEAD + (tid - 64), A.nx, A.ksz_x);
+  for (int i = tid; i < t_end - t_begin; i += RL_NT) sZ[i] = A.zmap[t_begin + R + i];
+  // vector path: every tile column is a real, contiguous, 16-byte aligned source column
+  const bool vec = (x0 - LEAD >= 0) && (x0 + RL_TX + LEAD <= A.nx) && ((A.nx & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(A.in) & 15u) == 0);
 
   float S[RL_CPT][K];
 #pragma unroll
@@ -74,29 +96,73 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
   double local_sum = 0.0;
   __syncthreads();
 
-  for (int t = zo0 - R; t < zo1 + R; ++t) {
-    const float* __restrict__ src = A.in + (size_t)A.zmap[t + R] * plane;
-    // ---- load the (AY x AX) input tile of this plane
-    for (int i = tid; i < AY * AX; i += RL_NT) {
-      int r = i / AX, c = i - r * AX;
-      sA[r * PA + c] = __ldg(src + sRowOff[r] + sCol[c]);
+  auto issue_plane = [&](int t, int buf) {
+    const float* __restrict__ src = A.in + (size_t)sZ[t - t_begin] * plane;
+    if (vec) {
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int i = tid + u * RL_NT;
+        const int r = i / CPR, q = i - r * CPR;
+        if (i < AY * CPR) cp_async16(&sA[buf][r * PA + q * 4], src + sRowOff[r] + (x0 - LEAD) + q * 4);
+      }
+    } else {
+#pragma unroll 2
+      for (int u = 0; u < NS; ++u) {
+        const int i = tid + u * RL_NT;
+        const int r = i / AX, c = i - r * AX;
+        if (i < AY * AX) cp_async4(&sA[buf][r * PA + c], src + sRowOff[r] + sCol[c]);
+      }
+    }
+    cp_async_commit();
+  };
+
+  issue_plane(t_begin, 0);
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    if (t + 1 < t_end) { issue_plane(t + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    // epilogue operands of the plane completed by this input plane: fetched now, consumed after the filters
+    const int z = t - R;
+    const bool emit = z >= zo0;
+    float eI[RL_CPT], eW[RL_CPT], eC[RL_CPT];
+    if (MODE != RL_PLAIN && emit) {
+#pragma unroll
+      for (int c = 0; c < RL_CPT; ++c) {
+        const int y = y0 + warp * 4 + c;
+        eI[c] = eW[c] = eC[c] = 0.f;
+        if (y < A.ny && x < A.nx) {
+          const size_t idx = (size_t)z * plane + (size_t)y * A.nx + x;
+          eW[c] = __ldg(A.weights + idx);
+          if (MODE == RL_RATIO)
+            eI[c] = A.view_u16 ? u16_to_float(__ldg(reinterpret_cast<const uint16_t*>(A.view) + idx))
+                               : __ldg(reinterpret_cast<const float*>(A.view) + idx);
+          if (MODE == RL_CORRECT) {
+            if (!A.first) eC[c] = A.out[idx];
+            if (A.last) eI[c] = A.est[A.est_off + idx];
+          }
+        }
+      }
     }
     __syncthreads();
-    // ---- x pass: strips of 4 outputs, 4 + 2R loaded values each
+    // ---- x pass: strips of 4 outputs; the window is read as whole 16-byte chunks (conflict free: the 8
+    // lanes of a quarter warp read 128 contiguous bytes of one tile row)
+    const float* tile = sA[buf];
     for (int item = tid; item < AY * (RL_TX / 4); item += RL_NT) {
       const int r = item >> 3, s = item & 7;
-      const float* a = sA + r * PA + s * 4;
-      float win[4 + 2 * R];
+      const float4* a = reinterpret_cast<const float4*>(tile + r * PA + s * 4);
+      float win[WIN];
 #pragma unroll
-      for (int j = 0; j < 4 + 2 * R; ++j) win[j] = a[j];
+      for (int j = 0; j < WIN / 4; ++j) {
+        const float4 v = a[j];
+        win[4 * j + 0] = v.x; win[4 * j + 1] = v.y; win[4 * j + 2] = v.z; win[4 * j + 3] = v.w;
+      }
       float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
 #pragma unroll
-      for (int j = 0; j < K; ++j) {  // out[x] = sum_j k[j] * in[x + 2R - j]  (tile-local columns)
+      for (int j = 0; j < K; ++j) {  // out[x] = sum_j k[j] * in[x + R - j]; tile column of x0+4s+i is LEAD+4s+i
         const float kj = A.kx[j];
-        o0 = fmaf(kj, win[0 + 2 * R - j], o0);
-        o1 = fmaf(kj, win[1 + 2 * R - j], o1);
-        o2 = fmaf(kj, win[2 + 2 * R - j], o2);
-        o3 = fmaf(kj, win[3 + 2 * R - j], o3);
+        o0 = fmaf(kj, win[LEAD + 0 + R - j], o0);
+        o1 = fmaf(kj, win[LEAD + 1 + R - j], o1);
+        o2 = fmaf(kj, win[LEAD + 2 + R - j], o2);
+        o3 = fmaf(kj, win[LEAD + 3 + R - j], o3);
       }
       float* b = sB + r * PB + s * 4;
       b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3;
@@ -115,8 +181,6 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
 #pragma unroll
         for (int c = 0; c < RL_CPT; ++c) p[c] = fmaf(kj, win[c + 2 * R - j], p[c]);
       }
-      const int z = t - R;  // the output plane completed by this input plane
-      const bool emit = z >= zo0;
 #pragma unroll
       for (int c = 0; c < RL_CPT; ++c) {
         const float e = fmaf(A.kz[0], p[c], S[c][0]);
@@ -130,18 +194,14 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
           if (MODE == RL_PLAIN) {
             A.out[idx] = blur;
           } else if (MODE == RL_RATIO) {
-            const float I = A.view_u16 ? u16_to_float(reinterpret_cast<const uint16_t*>(A.view)[idx])
-                                       : reinterpret_cast<const float*>(A.view)[idx];
-            const float w = A.weights[idx];
-            const float ratio = __fdiv_rn(I, blur + 1e-6f);
-            A.out[idx] = w > 1e-5f ? ratio : 0.f;
+            const float ratio = __fdiv_rn(eI[c], blur + 1e-6f);
+            A.out[idx] = eW[c] > 1e-5f ? ratio : 0.f;
           } else {
-            const float o = blur * A.weights[idx];
-            const float corr = A.first ? o : A.out[idx] + o;
+            const float o = blur * eW[c];
+            const float corr = A.first ? o : eC[c] + o;
             if (A.last) {
-              float* ep = A.est + A.est_off + idx;
-              const float v = fminf(fmaxf(*ep * corr, 0.f), 65535.f);
-              *ep = v;
+              const float v = fminf(fmaxf(eI[c] * corr, 0.f), 65535.f);
+              A.est[A.est_off + idx] = v;
               local_sum += (double)v;
             } else {
               A.out[idx] = corr;
@@ -150,7 +210,7 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
         }
       }
     }
-    // sA/sB are rewritten only after the next barrier pair; the y pass reads sB, the next load writes sA
+    // the y pass reads sB; sB is rewritten only after the next barrier, sA[buf] only by the plane after next
   }
   if (MODE == RL_CORRECT && A.last && A.sum) {
 #pragma unroll
@@ -199,12 +259,13 @@ static int padded_size(int k) {
 template <int MODE>
 static int launch_rl(int kp, const RLArgs& A, cudaStream_t st) {
   dim3 grid((A.nx + RL_TX - 1) / RL_TX, (A.ny + RL_TY - 1) / RL_TY, (A.nz + A.zchunk - 1) / A.zchunk);
+  const size_t zs = (size_t)(A.zchunk + kp - 1) * sizeof(int);
   switch (kp) {
-    case 7: rl_blur_kernel<7, MODE><<<grid, RL_NT, 0, st>>>(A); break;
-    case 13: rl_blur_kernel<13, MODE><<<grid, RL_NT, 0, st>>>(A); break;
-    case 19: rl_blur_kernel<19, MODE><<<grid, RL_NT, 0, st>>>(A); break;
-    case 25: rl_blur_kernel<25, MODE><<<grid, RL_NT, 0, st>>>(A); break;
-    case 31: rl_blur_kernel<31, MODE><<<grid, RL_NT, 0, st>>>(A); break;
+    case 7: rl_blur_kernel<7, MODE><<<grid, RL_NT, zs, st>>>(A); break;
+    case 13: rl_blur_kernel<13, MODE><<<grid, RL_NT, zs, st>>>(A); break;
+    case 19: rl_blur_kernel<19, MODE><<<grid, RL_NT, zs, st>>>(A); break;
+    case 25: rl_blur_kernel<25, MODE><<<grid, RL_NT, zs, st>>>(A); break;
+    case 31: rl_blur_kernel<31, MODE><<<grid, RL_NT, zs, st>>>(A); break;
     default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 31 taps");
   }
   MVF_LAUNCHED();
@@ -235,9 +296,10 @@ static int fill_rl(RLArgs& A, const float* in, const int32_t* zmap, const int32_
   A.nz = dims[0]; A.ny = dims[1]; A.nx = dims[2];
   // z chunk: enough CTAs to fill the GPU twice, at least 32 planes so the 2R-plane ramp-up stays small
   const int cols = ((A.nx + RL_TX - 1) / RL_TX) * ((A.ny + RL_TY - 1) / RL_TY);
-  int chunks = (2 * 2 * sm_count() + cols - 1) / cols;
+  int chunks = (6 * 2 * sm_count() + cols - 1) / cols;  // ~6 waves of 2 CTAs/SM: tail < 10 %
   int zc = (A.nz + chunks - 1) / chunks;
-  if (zc < 32) zc = 32;
+  if (zc < 64) zc = 64;                                // keeps the 2R-plane ramp-up of every chunk small
+  if (zc > 2048) zc = 2048;
   if (zc > A.nz) zc = A.nz;
   A.zchunk = zc;
   return MVF_OK;

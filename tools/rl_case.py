@@ -1,0 +1,18 @@
+"""Small driver for profiling one RL iteration (4 views, 512x1024x1024, 19^3 separable PSF)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from mvregfus_b200 import rl
+shape = tuple(int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (512, 1024, 1024)
+V = 4
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+views = [(torch.rand(shape, generator=g, device="cuda") * 3000).to(torch.int32).to(torch.uint16) for _ in range(V)]
+w = [torch.full(shape, 1.0 / V, device="cuda") for _ in range(V)]
+k = np.exp(-0.5 * (np.arange(-9, 10) / 6.0) ** 2); kz = (k / k.sum()).astype(np.float32)
+k = np.exp(-0.5 * (np.arange(-9, 10) / 2.0) ** 2); kxy = (k / k.sum()).astype(np.float32)
+psf = kz[:, None, None] * kxy[None, :, None] * kxy[None, None, :]
+plan = rl.RLPlan(views, w, [psf] * V)
+plan.init_estimate(); plan.iterate(); torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(); plan.iterate(); plan.iterate(); b.record(); torch.cuda.synchronize()
+print("ms/iteration", a.elapsed_time(b) / 2)
