@@ -124,17 +124,20 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
     const int z = t - R;
     const bool emit = z >= zo0;
     float eI[RL_CPT], eW[RL_CPT], eC[RL_CPT];
+    unsigned eRaw[RL_CPT];  // uint16 view voxels stay raw until the epilogue: converting here would wait for the load
     if (MODE != RL_PLAIN && emit) {
 #pragma unroll
       for (int c = 0; c < RL_CPT; ++c) {
         const int y = y0 + warp * 4 + c;
         eI[c] = eW[c] = eC[c] = 0.f;
+        eRaw[c] = 0u;
         if (y < A.ny && x < A.nx) {
           const size_t idx = (size_t)z * plane + (size_t)y * A.nx + x;
           eW[c] = __ldg(A.weights + idx);
-          if (MODE == RL_RATIO)
-            eI[c] = A.view_u16 ? u16_to_float(__ldg(reinterpret_cast<const uint16_t*>(A.view) + idx))
-                               : __ldg(reinterpret_cast<const float*>(A.view) + idx);
+          if (MODE == RL_RATIO) {
+            if (A.view_u16) eRaw[c] = __ldg(reinterpret_cast<const uint16_t*>(A.view) + idx);
+            else eI[c] = __ldg(reinterpret_cast<const float*>(A.view) + idx);
+          }
           if (MODE == RL_CORRECT) {
             if (!A.first) eC[c] = A.out[idx];
             if (A.last) eI[c] = A.est[A.est_off + idx];
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
           if (MODE == RL_PLAIN) {
             A.out[idx] = blur;
           } else if (MODE == RL_RATIO) {
-            const float ratio = __fdiv_rn(eI[c], blur + 1e-6f);
+            const float I = A.view_u16 ? u16_to_float(eRaw[c]) : eI[c];
+            const float ratio = __fdiv_rn(I, blur + 1e-6f);
             A.out[idx] = eW[c] > 1e-5f ? ratio : 0.f;
           } else {
             const float o = blur * eW[c];
