@@ -152,6 +152,18 @@ int mvf_rl_correct(const float* ratio, const int32_t* zmap, const int32_t dims[3
                    const float* weights, float* corr, int first, int last, float* est,
                    int64_t est_offset, double* sum_out, void* stream);
 
+/* ---- K3: DCT-entropy quality of blocks of a transformed view (determine_chunk_quality, mv:4496-4561) --
+ * For every job (linear index into the nblocks grid) the size^3 block is read with stride `bin` from the
+ * transformed view (zero beyond its extents), zero-filled like the reference, DCT-II(ortho)-transformed in
+ * float64 and reduced to q = -sum|d| log2(|d|/sum|d|); q_out[job block] receives the raw (un-normalised)
+ * value.  `cosm` is the size x size orthonormal DCT-II matrix (device, float64); `scratch` must hold
+ * mvf_dct_scratch_bytes(size) bytes.  Which views are inside a block and the normalisation over views are
+ * host decisions (blocks_inside, mv:4496-4508, 4548-4556). */
+int mvf_dct_scratch_bytes(int size, int* grid_out);
+int mvf_dct_entropy(const void* tview, int dtype, const int32_t dims[3], int bin, int size,
+                    const int32_t nblocks[3], const int32_t* jobs, int njobs, const double* cosm,
+                    double* scratch, double* q_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ EXPORTS = (
     "mvf_abi_version", "mvf_last_error", "mvf_launch_count",
     "mvf_affine_resample", "mvf_blend_weights", "mvf_fuse_weighted", "mvf_fuse_blend",
     "mvf_rl_padded_size", "mvf_rl_init_estimate", "mvf_rl_blur", "mvf_rl_ratio", "mvf_rl_correct",
+    "mvf_dct_scratch_bytes", "mvf_dct_entropy",
 )
 MVF_RL_KMAX = 31
 
@@ -78,9 +79,12 @@ def _declare(lib):
     lib.mvf_rl_ratio.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mvf_rl_correct.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.mvf_dct_scratch_bytes.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    lib.mvf_dct_entropy.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int, C.c_int, i32p, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version", "mvf_rl_padded_size"):
+        if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version", "mvf_rl_padded_size", "mvf_dct_scratch_bytes"):
             fn.restype = C.c_int
 
 

@@ -20,6 +20,7 @@ __all__ = [
     "get_weights_simple", "blocks_inside", "fuse_views_weights", "get_sample_volume", "get_union_volume",
     "calc_stack_properties_from_volume", "calc_stack_properties_from_views_and_params",
     "get_psf", "fuse_LR_with_weights_np",
+    "get_dct_options", "determine_chunk_quality", "get_weights_dct_dask", "get_weights_dct",
 ]
 
 
@@ -209,3 +210,78 @@ def fuse_LR_with_weights_np(views, params, stack_properties, num_iterations=25, 
     est = plan.run(num_iterations=num_iterations, tol=tol)
     est = est.cpu().numpy()
     return ImageArray(est.astype(np.uint16), spacing=stack_properties['spacing'], origin=stack_properties['origin'])
+
+
+# ---------------------------------------------------------------------------------------------------
+# a10-a12: DCT-entropy quality weights
+# ---------------------------------------------------------------------------------------------------
+def get_dct_options(spacing, size=None, max_kernel=None, gaussian_kernel=None):
+    """mv:3944-3958."""
+    from . import dct
+    return dct.get_dct_options(spacing, size, max_kernel, gaussian_kernel)
+
+
+def determine_chunk_quality(vrs, orig_stack_propertiess, params, stack_properties, block_info=None):
+    """DCT Shannon entropy of one (V, s, s, s) block, normalised over the views that see it; NaN for the others
+    (mv:4459-4561).  ``stack_properties`` carries the quality-grid spacing/origin; the block origin comes from
+    ``block_info[0]['array-location']`` exactly like the reference."""
+    from . import dct
+    vrs = np.asarray(vrs)
+    curr_origin = []
+    for i in range(3):
+        pixel_offset = block_info[0]['array-location'][i + 1][0]
+        curr_origin.append(stack_properties['origin'][i] + pixel_offset * stack_properties['spacing'][i])
+    bprops = {'size': np.array(vrs[0].shape).astype(np.int64), 'spacing': np.array(stack_properties['spacing']),
+              'origin': np.array(curr_origin)}
+    inside = blocks_inside(orig_stack_propertiess, params, bprops, n_points_per_dim=2)
+    nv = len(inside)
+    if not np.max(inside):
+        return (np.ones(nv).astype(np.float32) * np.nan)[:, None, None, None]
+    if np.sum(inside > 0) == 1:
+        ws = np.ones(nv).astype(np.float32) * np.nan
+        ws[inside > 0] = 1.
+        return ws[:, None, None, None]
+    size = int(vrs.shape[1])
+    if vrs.shape[1:] != (size, size, size):
+        raise Exception("determine_chunk_quality expects cubic blocks")
+    qs = []
+    for v in np.where(inside > 0)[0]:
+        q = dct.block_quality_device(fusion.to_device(vrs[v]), 1, size, [1, 1, 1], [0])
+        qs.append(q[0])
+    ws = np.array(qs)
+    if np.sum(ws) > 0:
+        ws = ws / np.sum(ws)
+    full = np.ones(nv) * np.nan
+    full[inside > 0] = ws
+    return full[:, None, None, None]
+
+
+def get_weights_dct_dask(tviews, params, orig_stack_propertiess, stack_properties, depth=0, size=None, max_kernel=None,
+                         gaussian_kernel=None, how_many_best_views=2, cumulative_weight_best_views=0.9):
+    """DCT-quality x blending weights of every 128^3 chunk (mv:4032-4457).
+
+    ``tviews``: (V, Z, Y, X) transformed views (numpy or dask), extents multiples of 128.  Returns the
+    (V, nz*(128+2d), ...) float32 array whose (V, 128+2*depth, ...) chunks fuse_block consumes; a dask array with
+    those chunks when dask is installed."""
+    from . import dct
+    arr = np.asarray(tviews)
+    dviews = [fusion.to_device(arr[v]) for v in range(arr.shape[0])]
+    chunks, _ = dct.weights_dct_chunks(dviews, params, orig_stack_propertiess, stack_properties, depth=depth,
+                                       max_kernel=max_kernel, how_many_best_views=how_many_best_views,
+                                       cumulative_weight_best_views=cumulative_weight_best_views)
+    edge = dct.CHUNK + 2 * depth
+    nchunks = [s // dct.CHUNK for s in arr.shape[1:]]
+    out = np.zeros([arr.shape[0]] + [n * edge for n in nchunks], dtype=np.float32)
+    for loc, w in chunks.items():
+        out[:, loc[0] * edge:(loc[0] + 1) * edge, loc[1] * edge:(loc[1] + 1) * edge, loc[2] * edge:(loc[2] + 1) * edge] = w.cpu().numpy()
+    return _maybe_dask(out, (arr.shape[0], edge, edge, edge))
+
+
+def get_weights_dct(views, params, orig_stack_propertiess, stack_properties, size=None, max_kernel=None,
+                    gaussian_kernel=None, how_many_best_views=1, cumulative_weight_best_views=0.9, block_info=None,
+                    array_info=None):
+    """The graph uses this name only as an identity tag for the DCT mode (mv:3729, mv_graph.py:336); called
+    directly it evaluates the DCT weights of the given (128-multiple) transformed views."""
+    return get_weights_dct_dask(np.asarray(views), params, orig_stack_propertiess, stack_properties, depth=0,
+                                max_kernel=max_kernel, how_many_best_views=how_many_best_views,
+                                cumulative_weight_best_views=cumulative_weight_best_views)
