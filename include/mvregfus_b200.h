@@ -127,6 +127,10 @@ typedef struct mvf_rl_psf {
   float ky[MVF_RL_KMAX];
   float kx[MVF_RL_KMAX];
   int32_t ksize[3];
+  /* A PSF that is not an outer product (oblique view) is passed densely instead: `dense` = device pointer to a
+   * Kp^3 float32 array, Kp = mvf_rl_padded_size(max ksize), the PSF centred and zero padded; the factors are
+   * then ignored and a direct (non-separable) convolution kernel runs.  NULL = use the factors. */
+  const float* dense;
 } mvf_rl_psf;
 
 /* kernel template size used for a PSF whose longest factor has k taps (7, 13, 19, 25 or 31; -1 if k > 31) */

@@ -48,7 +48,8 @@ class MvfView(C.Structure):
 
 class MvfRlPsf(C.Structure):
     """struct mvf_rl_psf: separable PSF factors (true-convolution taps)."""
-    _fields_ = [("kz", C.c_float * 31), ("ky", C.c_float * 31), ("kx", C.c_float * 31), ("ksize", C.c_int32 * 3)]
+    _fields_ = [("kz", C.c_float * 31), ("ky", C.c_float * 31), ("kx", C.c_float * 31), ("ksize", C.c_int32 * 3),
+                ("dense", C.c_void_p)]
 
 
 _lock = threading.Lock()

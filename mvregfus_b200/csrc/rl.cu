@@ -37,6 +37,8 @@ struct RLArgs {
   float* est;           // CORRECT+last: estimate planes (may live in a halo-padded buffer)
   long long est_off;    // element offset of output plane 0 inside `est`
   double* sum;          // CORRECT+last: sum(est) accumulated here (convergence test, mv:5726)
+  const float* dense;   // non-separable PSF: Kp^3 taps (device), centred and zero padded
+  int ksz_z;            // original z size (direct kernel: index map offsets)
 };
 
 // index map of the reference's boundary handling: reflect (no edge repeat) above, wrap into
@@ -223,6 +225,67 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
   }
 }
 
+// Direct (non-separable) convolution for PSFs of oblique views: every thread produces 4 consecutive x outputs,
+// walking the Kp^2 (z,y) tap rows with a (Kp+3)-wide register window per row.  O(K^3) per voxel: the fallback
+// for PSFs that are not outer products (the separable kernel above is the fast path).
+template <int K, int MODE>
+__global__ void __launch_bounds__(256) rl_direct_kernel(const __grid_constant__ RLArgs A) {
+  constexpr int R = (K - 1) / 2;
+  const int xq = blockIdx.x * 32 + (threadIdx.x & 31);   // group of 4 x outputs
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int z = blockIdx.z;
+  const int x0 = xq * 4;
+  if (y >= A.ny || x0 >= A.nx) return;
+  const size_t plane = (size_t)A.ny * A.nx;
+  int cols[K + 3];
+#pragma unroll
+  for (int j = 0; j < K + 3; ++j) cols[j] = ext_index(x0 - R + j, A.nx, A.ksz_x);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int jz = 0; jz < K; ++jz) {
+    const float* __restrict__ src = A.in + (size_t)A.zmap[z + R - jz + R] * plane;  // zmap[t + Rp], t = z + R - jz
+    for (int jy = 0; jy < K; ++jy) {
+      const float* __restrict__ row = src + (size_t)ext_index(y + R - jy, A.ny, A.ksz_y) * A.nx;
+      const float* __restrict__ taps = A.dense + (jz * K + jy) * K;
+      float win[K + 3];
+#pragma unroll
+      for (int j = 0; j < K + 3; ++j) win[j] = __ldg(row + cols[j]);
+#pragma unroll
+      for (int jx = 0; jx < K; ++jx) {
+        const float kj = __ldg(taps + jx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(kj, win[i + 2 * R - jx], acc[i]);
+      }
+    }
+  }
+  double local_sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x0 + i;
+    if (x >= A.nx) break;
+    const size_t idx = (size_t)z * plane + (size_t)y * A.nx + x;
+    const float blur = fmaxf(acc[i], 0.f);
+    if (MODE == RL_PLAIN) {
+      A.out[idx] = blur;
+    } else if (MODE == RL_RATIO) {
+      const float I = A.view_u16 ? u16_to_float(reinterpret_cast<const uint16_t*>(A.view)[idx])
+                                 : reinterpret_cast<const float*>(A.view)[idx];
+      const float ratio = __fdiv_rn(I, blur + 1e-6f);
+      A.out[idx] = A.weights[idx] > 1e-5f ? ratio : 0.f;
+    } else {
+      const float o = blur * A.weights[idx];
+      const float corr = A.first ? o : A.out[idx] + o;
+      if (A.last) {
+        const float v = fminf(fmaxf(A.est[A.est_off + idx] * corr, 0.f), 65535.f);
+        A.est[A.est_off + idx] = v;
+        local_sum += (double)v;
+      } else {
+        A.out[idx] = corr;
+      }
+    }
+  }
+  if (MODE == RL_CORRECT && A.last && A.sum) atomicAdd(A.sum, local_sum);
+}
+
 // estimate = sum_v w_v * I_v in float32, views added in order (np.sum(weights * data, 0), mv:5629)
 struct RLInitArgs {
   const void* views[MVF_MAX_VIEWS];
@@ -261,7 +324,23 @@ static int padded_size(int k) {
 }
 
 template <int MODE>
+static int launch_rl_direct(int kp, const RLArgs& A, cudaStream_t st) {
+  dim3 grid((A.nx + 127) / 128, (A.ny + 7) / 8, A.nz);
+  switch (kp) {
+    case 7: rl_direct_kernel<7, MODE><<<grid, 256, 0, st>>>(A); break;
+    case 13: rl_direct_kernel<13, MODE><<<grid, 256, 0, st>>>(A); break;
+    case 19: rl_direct_kernel<19, MODE><<<grid, 256, 0, st>>>(A); break;
+    case 25: rl_direct_kernel<25, MODE><<<grid, 256, 0, st>>>(A); break;
+    case 31: rl_direct_kernel<31, MODE><<<grid, 256, 0, st>>>(A); break;
+    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "PSF longer than 31 taps");
+  }
+  MVF_LAUNCHED();
+  return MVF_OK;
+}
+
+template <int MODE>
 static int launch_rl(int kp, const RLArgs& A, cudaStream_t st) {
+  if (A.dense) return launch_rl_direct<MODE>(kp, A, st);
   dim3 grid((A.nx + RL_TX - 1) / RL_TX, (A.ny + RL_TY - 1) / RL_TY, (A.nz + A.zchunk - 1) / A.zchunk);
   const size_t zs = (size_t)(A.zchunk + kp - 1) * sizeof(int);
   switch (kp) {
@@ -296,7 +375,8 @@ static int fill_rl(RLArgs& A, const float* in, const int32_t* zmap, const int32_
     for (int j = 0; j < psf->ksize[d]; ++j) dst[d][pad + j] = taps[d][j];
   }
   A.in = in; A.zmap = zmap;
-  A.ksz_y = psf->ksize[1]; A.ksz_x = psf->ksize[2];
+  A.dense = psf->dense;
+  A.ksz_z = psf->ksize[0]; A.ksz_y = psf->ksize[1]; A.ksz_x = psf->ksize[2];
   A.nz = dims[0]; A.ny = dims[1]; A.nx = dims[2];
   // z chunk: enough CTAs to fill the GPU twice, at least 32 planes so the 2R-plane ramp-up stays small
   const int cols = ((A.nx + RL_TX - 1) / RL_TX) * ((A.ny + RL_TY - 1) / RL_TY);

@@ -28,6 +28,22 @@ def factor_psf(psf, tol=2e-6):
     return (kz / total).astype(np.float32), (ky / total).astype(np.float32), kx.astype(np.float32)
 
 
+def make_dense_psf_struct(psf, device):
+    """Non-separable PSF: centred, zero padded to Kp^3 and uploaded; returns (struct, tensor to keep alive)."""
+    psf = np.asarray(psf, dtype=np.float32)
+    kp = _cabi.load().mvf_rl_padded_size(int(max(psf.shape)))
+    if kp < 0 or any(k % 2 == 0 for k in psf.shape):
+        raise ValueError("PSF sizes must be odd and <= %d" % _cabi.MVF_RL_KMAX)
+    full = np.zeros((kp, kp, kp), dtype=np.float32)
+    o = [(kp - k) // 2 for k in psf.shape]
+    full[o[0]:o[0] + psf.shape[0], o[1]:o[1] + psf.shape[1], o[2]:o[2] + psf.shape[2]] = psf
+    t = torch.from_numpy(full).to(device)
+    s = _cabi.MvfRlPsf()
+    s.ksize = _cabi.i32x3(psf.shape)
+    s.dense = t.data_ptr()
+    return s, t
+
+
 def make_psf_struct(factors):
     s = _cabi.MvfRlPsf()
     for name, k in zip(("kz", "ky", "kx"), factors):
@@ -69,15 +85,19 @@ class RLPlan:
         self.n = len(views)
         self.dims = tuple(int(s) for s in views[0].shape)
         dev = views[0].device
-        self.factors = []
+        self.psf_structs, self.zmaps, self.separable, self._keep = [], [], [], []
         for p in psfs:
             f = factor_psf(p)
-            if f is None:
-                raise NotImplementedError(
-                    "non-separable PSF (view not axis aligned): the FFT path is not built yet in this round")
-            self.factors.append(f)
-        self.psf_structs = [make_psf_struct(f) for f in self.factors]
-        self.zmaps = [torch.from_numpy(zmap_whole(self.dims[0], len(f[0]), padded_radius(f))).to(dev) for f in self.factors]
+            self.separable.append(f is not None)
+            if f is not None:  # outer-product PSF (axis-aligned view): fused separable kernel
+                self.psf_structs.append(make_psf_struct(f))
+                ksz, rp = len(f[0]), padded_radius(f)
+            else:              # oblique view: dense PSF, direct convolution kernel
+                st, keep = make_dense_psf_struct(p, dev)
+                self.psf_structs.append(st)
+                self._keep.append(keep)
+                ksz, rp = int(np.asarray(p).shape[0]), (int(keep.shape[0]) - 1) // 2
+            self.zmaps.append(torch.from_numpy(zmap_whole(self.dims[0], ksz, rp)).to(dev))
         self.est = torch.empty(self.dims, dtype=torch.float32, device=dev)
         self.ratio = torch.empty(self.dims, dtype=torch.float32, device=dev)
         self.corr = torch.empty(self.dims, dtype=torch.float32, device=dev)

@@ -1,0 +1,53 @@
+"""fuse_block / fuse_blockwise control flow on the GPU wrappers against the oracle and the reference golden."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mvregfus_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
+
+
+@pytest.mark.parametrize("tag", ["all", "one"])
+@pytest.mark.parametrize("ftag", ["wavg", "lr"])
+def test_fuse_block_matches_reference_golden(cuda, tag, ftag):
+    from mvregfus_b200 import multiview as mv
+    tv = G["block_tviews"].copy()
+    if tag == "one":
+        tv[0] = 0
+        tv[2] = 0
+    props = [{"size": np.array([60, 60, 60]), "spacing": np.ones(3), "origin": np.array([-10.0, -10.0, -10.0])}
+             for _ in range(3)]
+    spb = {"size": np.array([128, 128, 128]), "spacing": np.ones(3), "origin": np.zeros(3)}
+    ff, kw = (mv.fuse_views_weights, {}) if ftag == "wavg" else \
+        (mv.fuse_LR_with_weights_np, {"num_iterations": 2, "sz": 2, "sxy": 1, "tol": 5e-5})
+    res = np.asarray(mv.fuse_block(tv, None, G["block_params"], dict(spb), props, {"depth": 4, "chunksize": 32},
+                                   mv.get_weights_simple, ff, {}, dict(kw), block_info={0: {"chunk-location": (0, 0, 0, 0)}}))
+    ref = G["block_%s_%s" % (tag, ftag)]
+    assert res.shape == ref.shape and res.dtype == ref.dtype
+    d = np.abs(res.astype(np.int64) - ref.astype(np.int64))
+    if tag == "one":
+        assert d.max() == 0  # raw copy of the only live view
+    else:
+        assert d.max() <= 3 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
+
+
+def test_fuse_blockwise_arrays(cuda):
+    """Two 128-chunks along x with an 8-voxel halo, blending weights + weighted average."""
+    from mvregfus_b200 import multiview as mv
+    from tests.golden.make_golden import blob_volume, case_params
+    shape = (40, 48, 150)
+    params = case_params((40, 48, 150), 2, seed=7, odd_extra_deg=0.0)
+    params[1][:9] = params[0][:9]
+    params[1][9:] = params[0][9:] + np.array([3.0, -2.0, 20.0])
+    props = [{"size": np.array(shape), "spacing": np.ones(3), "origin": np.zeros(3)} for _ in range(2)]
+    sp = {"size": np.array(shape), "spacing": np.ones(3), "origin": np.zeros(3)}
+    tv = [blob_volume(shape, 300 + i, np.uint16, 0.3) for i in range(2)]
+    ref = O.fuse_blockwise(tv, params, sp, props, fusion_block_overlap=8)
+    got = mv.fuse_blockwise_arrays(tv, params, sp, props, fusion_block_overlap=8,
+                                   weights_func=mv.get_weights_simple, fusion_func=mv.fuse_views_weights)
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 2 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
