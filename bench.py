@@ -124,7 +124,7 @@ RL_SIGMA = (6.0, 2.0)  # sz, sxy  -> 19^3 PSF at spacing 1 (BASELINE.json config
 RL_ITERS = 10
 
 
-def run_rl(dev, steps_cap=1):
+def run_rl(dev, rank=0, world=1):
     """BASELINE.json configs[3]: 4 views 1024x1024x512 uint16, Gaussian PSF sigma 2x2x6, 10 RL iterations, on the
     transformed views and blending weights produced by the fusion kernels.  Returns the `rl` JSON object."""
     import torch
@@ -156,11 +156,24 @@ def run_rl(dev, steps_cap=1):
     vs = fusion.build_viewset(None, props, params, sp, weights="blending")
     w = fusion.blend_weights(vs, shape, normalise=True)
     psfs = [mv.get_psf(params[v], sp, RL_SIGMA[0], RL_SIGMA[1]) for v in range(NVIEWS)]
-    plan = rl.RLPlan(tviews, [w[v] for v in range(NVIEWS)], psfs)
+    if world == 1:
+        plan = rl.RLPlan(tviews, [w[v] for v in range(NVIEWS)], psfs)
+    else:  # z-slab of this rank; PSF-radius halos are exchanged over NCCL inside plan.iterate()
+        import torch.distributed as dist
+        from mvregfus_b200 import slab
+        z0, z1 = slab.slab_bounds(shape[0], world)[rank]
+        tv_slab = [t[z0:z1].clone() for t in tviews]
+        w_slab = [w[v][z0:z1].clone() for v in range(NVIEWS)]
+        del tviews, w
+        torch.cuda.empty_cache()
+        plan = rl.SlabRLPlan(tv_slab, w_slab, psfs, shape[0], rank, world)
     plan.init_estimate()
     plan.iterate()  # warm-up
     torch.cuda.synchronize()
     plan.init_estimate()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(RL_ITERS):
@@ -168,6 +181,10 @@ def run_rl(dev, steps_cap=1):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     nvox = int(np.prod(shape))
     peak, how = measured_peak_gbs()
     alg = (12 + NVIEWS * (16 + 2)) * nvox
@@ -175,9 +192,10 @@ def run_rl(dev, steps_cap=1):
     return {"metric": "rl_iterations_per_s", "value": 1e3 / per_it, "unit": "it/s", "ms_per_iteration": per_it,
             "config": {"workload": "BASELINE.json configs[3]: %d views %dx%dx%d uint16 in the fused frame, Gaussian PSF "
                                    "sigma z=%g xy=%g (19^3, separable), %d iterations" % (NVIEWS, *shape, *RL_SIGMA, RL_ITERS)},
-            "kernel_launches_per_iteration": 2 * NVIEWS,
-            "roofline": {"bound": "hbm", "achieved": alg / (per_it * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (per_it * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_iteration": alg,
+            "kernel_launches_per_iteration": 2 * NVIEWS, "n_gpus": world,
+            "sharding": "whole volume" if world == 1 else "z-slabs, ring halo exchange (%d planes) over NCCL before every blur, strong scaling" % ((19 - 1) // 2),
+            "roofline": {"bound": "hbm", "achieved": alg / (per_it * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": alg / (per_it * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes_per_iteration": alg,
                          "peak_source": how}}
 
 
@@ -352,16 +370,20 @@ def run_b200(args):
                              "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                              "kernel": "fuse_blend_kernel<float,4>", "kernel_ms": kernel_ms,
                              "algorithmic_bytes": alg_bytes}}
-        if not args.skip_rl and world == 1:
+        if not args.skip_rl:
             del views, dviews, vs, vs2, out
             torch.cuda.empty_cache()
-            line["rl"] = run_rl(dev)
+            line["rl"] = run_rl(dev, rank, world)
         if not args.no_cpu_baseline:
             views_host = [p.numpy() for p in pinned]
             gv, dt, sample = cpu_baseline(views_host, params, props, sp, box=96, threads=1)
             line["cpu_baseline"] = {"value": gv, "unit": "Gvoxel/s", "cores": 1, "kind": "port", "sample": sample,
                                     "seconds": dt}
         print(json.dumps(line))
+    if rank != 0 and world > 1 and not args.skip_rl:
+        del views, dviews, vs, vs2, out
+        torch.cuda.empty_cache()
+        run_rl(dev, rank, world)
     if world > 1:
         dist.destroy_process_group()
 

@@ -160,3 +160,104 @@ def blur(volume, psf_factors):
     _cabi.check(lib.mvf_rl_blur(C.c_void_p(volume.data_ptr()), C.c_void_p(zm.data_ptr()), _cabi.i32x3(dims), C.byref(ps),
                                 C.c_void_p(out.data_ptr()), _stream_ptr()))
     return out
+
+
+class SlabRLPlan:
+    """Multi-view RL on one z-slab of the fused frame (one rank of a box): halo-padded estimate / ratio buffers,
+    ring halo exchange over torch.distributed before every blur, scalar all-reduce for the convergence test."""
+
+    def __init__(self, views, weights, psfs, nz_total, rank, world, group=None):
+        from . import slab
+        self.lib = _cabi.load()
+        self.views, self.weights, self.group = views, weights, group
+        self.n = len(views)
+        dev = views[0].device
+        nzl, ny, nx = (int(s) for s in views[0].shape)
+        shapes = {tuple(np.asarray(p).shape) for p in psfs}
+        if len(shapes) != 1:
+            raise ValueError("all views must share one PSF shape")
+        kz = next(iter(shapes))[0]
+        self.psf_structs, self._keep = [], []
+        rp = None
+        for p in psfs:
+            f = factor_psf(p)
+            if f is not None:
+                self.psf_structs.append(make_psf_struct(f))
+                r = padded_radius(f)
+            else:
+                st, keep = make_dense_psf_struct(p, dev)
+                self.psf_structs.append(st)
+                self._keep.append(keep)
+                r = (int(keep.shape[0]) - 1) // 2
+            rp = r if rp is None else rp
+            if r != rp:
+                raise ValueError("PSFs need one common padded size")
+        self.halo = slab.HaloPlan(nz_total, world, rank, kz, rp)
+        if self.halo.nzl != nzl:
+            raise ValueError("slab height %d does not match the planner's %d" % (nzl, self.halo.nzl))
+        self.rp, self.dims = rp, (nzl, ny, nx)
+        self.zmap = torch.from_numpy(self.halo.zmap()).to(dev)
+        self.est_pad = torch.zeros((nzl + 2 * rp, ny, nx), dtype=torch.float32, device=dev)
+        self.ratio_pad = torch.zeros((nzl + 2 * rp, ny, nx), dtype=torch.float32, device=dev)
+        self.est = self.est_pad[rp:rp + nzl]
+        self.ratio = self.ratio_pad[rp:rp + nzl]
+        self.corr = torch.empty(self.dims, dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(2, dtype=torch.float64, device=dev)
+        self._vp = (C.c_void_p * self.n)(*[v.data_ptr() for v in views])
+        self._wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in weights])
+        self._dims = _cabi.i32x3(self.dims)
+        self._est_off = rp * ny * nx
+
+    def init_estimate(self):
+        self.sums.zero_()
+        _cabi.check(self.lib.mvf_rl_init_estimate(self.n, self._vp, dtype_code(self.views[0]), self._wp,
+                                                  C.c_void_p(self.est.data_ptr()), self.est.numel(),
+                                                  C.c_void_p(self.sums.data_ptr()), _stream_ptr()))
+
+    def step_ratio(self, v):
+        """R_v = I_v / (blur(est) + 1e-6) * mask, read from the halo-padded estimate."""
+        _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
+                                          C.byref(self.psf_structs[v]), C.c_void_p(self.views[v].data_ptr()),
+                                          dtype_code(self.views[v]), C.c_void_p(self.weights[v].data_ptr()),
+                                          C.c_void_p(self.ratio.data_ptr()), _stream_ptr()))
+
+    def step_correct(self, v):
+        """C (+)= blur(R_v) * w_v; the last view applies the multiplicative update to the estimate."""
+        last = v == self.n - 1
+        _cabi.check(self.lib.mvf_rl_correct(C.c_void_p(self.ratio_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
+                                            C.byref(self.psf_structs[v]), C.c_void_p(self.weights[v].data_ptr()),
+                                            C.c_void_p(self.corr.data_ptr()), 1 if v == 0 else 0, 1 if last else 0,
+                                            C.c_void_p(self.est_pad.data_ptr()), self._est_off,
+                                            C.c_void_p(self.sums[1:].data_ptr()), _stream_ptr()))
+
+    def iterate(self):
+        from . import slab
+        self.sums[1:].zero_()
+        slab.exchange_halos(self.est_pad, self.halo, self.group)     # one exchange serves all views' first blur
+        for v in range(self.n):
+            self.step_ratio(v)
+            slab.exchange_halos(self.ratio_pad, self.halo, self.group)
+            self.step_correct(v)
+
+    def run(self, num_iterations=25, tol=5e-5):
+        import torch.distributed as dist
+        self.init_estimate()
+        curr = None
+        i = 0
+        while True:
+            self.iterate()
+            if i >= 10:
+                s = self.sums.clone()
+                if self.halo.world > 1:
+                    dist.all_reduce(s, group=self.group)
+                s = s.cpu().numpy()
+                curr = s[0] if curr is None else curr
+                if abs(1 - s[1] / curr) < tol:
+                    break
+                curr = s[1]
+            else:
+                self.sums[0] = self.sums[1]
+            if i >= num_iterations - 1:
+                break
+            i += 1
+        return self.est

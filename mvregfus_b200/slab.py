@@ -1,0 +1,112 @@
+"""z-slab sharding of the fused frame across the GPUs of one box.
+
+Resampling, weights and weighted fusion are pointwise in the fused frame, so a rank simply produces the index
+box ``[z0, z1) x ny x nx`` (``out_origin``/``out_dims`` of the C-ABI): no data-path collective.  Multi-view RL
+needs the PSF-radius halo planes of its convolution inputs: a ring exchange (rank 0's lower halo comes from the
+last rank because of the reference's wrap-around boundary) plus one scalar all-reduce for the
+convergence test.  Everything here is host logic + torch.distributed; it runs on CPU tensors with gloo in the
+tests and on CUDA tensors with NCCL on the box.
+"""
+import numpy as np
+import torch
+
+
+def slab_bounds(nz, world):
+    """Contiguous z ranges [(z0, z1)] of `world` slabs, sizes differing by at most one plane."""
+    base, rem = divmod(int(nz), int(world))
+    bounds, z = [], 0
+    for r in range(world):
+        h = base + (1 if r < rem else 0)
+        bounds.append((z, z + h))
+        z += h
+    return bounds
+
+
+def source_brick(matrix, offset, view_shape, z0, z1, ny, nx):
+    """Index box of a view that the slab [z0,z1) touches: the reference's own chunk bounding box (corners
+    through matrix', +-2, clipped; mv:1552-1571) applied to the slab.  Returns (lo[3], hi[3]) int64."""
+    corners = np.array([[z, y, x] for z in (z0, z1) for y in (0, ny) for x in (0, nx)], dtype=np.float64)
+    src = corners @ np.asarray(matrix, dtype=np.float64).T + np.asarray(offset, dtype=np.float64)
+    lo = np.clip(src.min(0) - 2, 0, view_shape).astype(np.int64)
+    hi = np.clip(src.max(0) + 2, 0, view_shape).astype(np.int64)
+    return lo, hi
+
+
+def _ext(t, n, K):
+    """Reference boundary index map (reflect above, wrap into the far reflected tail below), clamped."""
+    i = np.where(t < 0, n - 3 - K - t, np.where(t >= n, 2 * n - 2 - t, t))
+    return np.clip(i, 0, n - 1)
+
+
+class HaloPlan:
+    """Plane bookkeeping of one rank's halo-padded slab buffer: planes [0,rp) = lower halo, [rp, rp+nzl) = own
+    planes, [rp+nzl, nzl+2rp) = upper halo."""
+
+    def __init__(self, nz, world, rank, ksize_z, rp):
+        self.nz, self.world, self.rank, self.K, self.rp = int(nz), int(world), int(rank), int(ksize_z), int(rp)
+        self.bounds = slab_bounds(nz, world)
+        self.z0, self.z1 = self.bounds[rank]
+        self.nzl = self.z1 - self.z0
+        if world > 1 and min(b - a for a, b in self.bounds) < max(2 * rp + 1, ksize_z + 3 + rp):
+            raise ValueError("slabs of %d planes are too thin for a halo of %d planes" % (min(b - a for a, b in self.bounds), rp))
+        self.lower_src = (rank - 1) % world   # ring: rank 0's lower halo comes from the last rank
+        self.upper_src = rank + 1 if rank + 1 < world else None
+
+    def zmap(self):
+        """Extended local position t in [-rp, nzl+rp) -> plane of the padded buffer."""
+        t = np.arange(-self.rp, self.nzl + self.rp)
+        g = self.z0 + t
+        plane = t + self.rp                                   # default: own planes / halos filled by neighbours
+        if self.world == 1:
+            return (_ext(g, self.nz, self.K) + self.rp).astype(np.int32)
+        above = g >= self.nz                                  # top rank: reflection inside its own slab
+        plane = np.where(above, _ext(g, self.nz, self.K) - self.z0 + self.rp, plane)
+        # g < 0 (rank 0): the lower halo planes hold what the last rank sent (wrap), same positions
+        return np.clip(plane, 0, self.nzl + 2 * self.rp - 1).astype(np.int32)
+
+    def planes_for_upper_neighbour(self):
+        """Own-plane indices (0-based within the slab) that fill the LOWER halo of rank+1 (or of rank 0 when this
+        is the last rank), in halo order."""
+        if self.rank + 1 < self.world:
+            return np.arange(self.nzl - self.rp, self.nzl)
+        g = np.arange(-self.rp, 0)                             # rank 0's positions below the volume
+        return _ext(g, self.nz, self.K) - self.z0              # wrap into this (last) rank's slab
+
+    def planes_for_lower_neighbour(self):
+        """Own-plane indices that fill the UPPER halo of rank-1 (none for rank 0)."""
+        return np.arange(0, self.rp) if self.rank > 0 else None
+
+
+def exchange_halos(buf, plan, group=None):
+    """Fill the halo planes of `buf` ((nzl+2rp, ny, nx), own planes already written) from the ring neighbours."""
+    import torch.distributed as dist
+    rp, nzl = plan.rp, plan.nzl
+    if plan.world == 1:
+        return
+    up_idx = torch.as_tensor(plan.planes_for_upper_neighbour() + rp, device=buf.device, dtype=torch.long)
+    send_up = buf.index_select(0, up_idx).contiguous()
+    ops = [dist.P2POp(dist.isend, send_up, (plan.rank + 1) % plan.world, group=group),
+           dist.P2POp(dist.irecv, buf[0:rp], plan.lower_src, group=group)]
+    if plan.rank > 0:
+        send_down = buf[rp:2 * rp].contiguous()
+        ops.append(dist.P2POp(dist.isend, send_down, plan.rank - 1, group=group))
+    if plan.upper_src is not None:
+        ops.append(dist.P2POp(dist.irecv, buf[rp + nzl:rp + nzl + rp], plan.upper_src, group=group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def exchange_halos_local(bufs, plans):
+    """The same plane movement as :func:`exchange_halos` between the buffers of ranks emulated in ONE process
+    (tests on a single GPU): bufs[r] / plans[r] belong to emulated rank r."""
+    world = len(plans)
+    if world == 1:
+        return
+    for r, (buf, plan) in enumerate(zip(bufs, plans)):
+        rp, nzl = plan.rp, plan.nzl
+        src = plan.lower_src
+        idx = torch.as_tensor(plans[src].planes_for_upper_neighbour() + plans[src].rp, device=buf.device, dtype=torch.long)
+        buf[0:rp] = bufs[src].index_select(0, idx)
+        if plan.upper_src is not None:
+            up = plan.upper_src
+            buf[rp + nzl:rp + nzl + rp] = bufs[up][plans[up].rp:2 * plans[up].rp]
