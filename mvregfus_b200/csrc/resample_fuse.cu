@@ -551,8 +551,10 @@ __global__ void __launch_bounds__(NT, MVF_MINB) fuse_blend_kernel(const __grid_c
   int z0, y0, x0;
   if (!tile_origin(A.dims, z0, y0, x0)) return;
   const int tid = threadIdx.x;
-  if (tid < A.nviews)
+  if (tid < A.nviews) {
     make_tile_view<sizeof(T)>(A.v[tid], z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], true, tv[tid]);
+    if (tv[tid].wclass == WT_ZERO) tv[tid].skip = 1;  // zero weight on the whole tile: the view contributes nothing
+  }
   __syncthreads();
   const int y = y0 + (tid >> 5), x = x0 + (tid & 31);                        // local (box) index
   const int gz = z0 + A.org[0], gy = y + A.org[1], gx = x + A.org[2];        // fused-frame index of voxel k=0
@@ -581,14 +583,16 @@ __global__ void __launch_bounds__(NT, MVF_MINB) fuse_blend_kernel(const __grid_c
     while (vn < A.nviews && tv[vn].skip) ++vn;
     if (vn < A.nviews) prefetch_brick<T>(A.v[vn], tv[vn], q);
     const float* wv = wsm + v * TZ * NT + tid;
-    auto sink = [&](int k, float vv) {
-      float wn = __fdiv_rn(wv[k * NT], wsum[k]);
-      if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));  // the transformed view is uint16 (mv:1626)
-      acc[k] += trunc_product_u16(wn, vv);
-      if (WANT_F32) accf[k] = fmaf(wn, vv, accf[k]);
-    };
-    if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, sink);
-    else column_gather<false>(sm, t, kv, gz, gy, gx, sink);
+    {
+      auto sink = [&](int k, float vv) {
+        float wn = __fdiv_rn(wv[k * NT], wsum[k]);
+        if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));
+        acc[k] += trunc_product_u16(wn, vv);
+        if (WANT_F32) accf[k] = fmaf(wn, vv, accf[k]);
+      };
+      if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, sink);
+      else column_gather<false>(sm, t, kv, gz, gy, gx, sink);
+    }
     v = vn;
   }
 

@@ -98,15 +98,22 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
   double local_sum = 0.0;
   __syncthreads();
 
+  // per-thread copy descriptors, computed once: offset inside a source plane and inside a tile buffer
+  int goff[NV], soff[NV];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int i = tid + u * RL_NT;
+    const int r = i / CPR, q = i - r * CPR;
+    const bool ok = vec && i < AY * CPR;
+    goff[u] = ok ? sRowOff[r] + (x0 - LEAD) + q * 4 : -1;
+    soff[u] = r * PA + q * 4;
+  }
   auto issue_plane = [&](int t, int buf) {
     const float* __restrict__ src = A.in + (size_t)sZ[t - t_begin] * plane;
     if (vec) {
 #pragma unroll
-      for (int u = 0; u < NV; ++u) {
-        const int i = tid + u * RL_NT;
-        const int r = i / CPR, q = i - r * CPR;
-        if (i < AY * CPR) cp_async16(&sA[buf][r * PA + q * 4], src + sRowOff[r] + (x0 - LEAD) + q * 4);
-      }
+      for (int u = 0; u < NV; ++u)
+        if (goff[u] >= 0) cp_async16(&sA[buf][soff[u]], src + goff[u]);
     } else {
 #pragma unroll 2
       for (int u = 0; u < NS; ++u) {
@@ -117,6 +124,19 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
     }
     cp_async_commit();
   };
+
+  // epilogue addressing: offset of the thread's 4 columns inside a plane (-1: outside the volume)
+  int coff[RL_CPT];
+#pragma unroll
+  for (int c = 0; c < RL_CPT; ++c) {
+    const int y = y0 + warp * 4 + c;
+    coff[c] = (y < A.ny && x < A.nx) ? y * A.nx + x : -1;
+  }
+  const float* __restrict__ wplane = A.weights ? A.weights + (size_t)zo0 * plane : nullptr;
+  float* __restrict__ oplane = A.out ? A.out + (size_t)zo0 * plane : nullptr;
+  float* __restrict__ eplane = A.est ? A.est + A.est_off + (size_t)zo0 * plane : nullptr;
+  const unsigned char* vplane = A.view ? reinterpret_cast<const unsigned char*>(A.view) + (size_t)zo0 * plane * (A.view_u16 ? 2 : 4) : nullptr;
+  const size_t vstep = plane * (A.view_u16 ? 2 : 4);
 
   issue_plane(t_begin, 0);
   for (int t = t_begin; t < t_end; ++t) {
@@ -130,19 +150,17 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
     if (MODE != RL_PLAIN && emit) {
 #pragma unroll
       for (int c = 0; c < RL_CPT; ++c) {
-        const int y = y0 + warp * 4 + c;
         eI[c] = eW[c] = eC[c] = 0.f;
         eRaw[c] = 0u;
-        if (y < A.ny && x < A.nx) {
-          const size_t idx = (size_t)z * plane + (size_t)y * A.nx + x;
-          eW[c] = __ldg(A.weights + idx);
+        if (coff[c] >= 0) {
+          eW[c] = __ldg(wplane + coff[c]);
           if (MODE == RL_RATIO) {
-            if (A.view_u16) eRaw[c] = __ldg(reinterpret_cast<const uint16_t*>(A.view) + idx);
-            else eI[c] = __ldg(reinterpret_cast<const float*>(A.view) + idx);
+            if (A.view_u16) eRaw[c] = __ldg(reinterpret_cast<const uint16_t*>(vplane) + coff[c]);
+            else eI[c] = __ldg(reinterpret_cast<const float*>(vplane) + coff[c]);
           }
           if (MODE == RL_CORRECT) {
-            if (!A.first) eC[c] = A.out[idx];
-            if (A.last) eI[c] = A.est[A.est_off + idx];
+            if (!A.first) eC[c] = oplane[coff[c]];
+            if (A.last) eI[c] = eplane[coff[c]];
           }
         }
       }
@@ -192,29 +210,33 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
 #pragma unroll
         for (int m = 0; m < K - 1; ++m) S[c][m] = fmaf(A.kz[m + 1], p[c], S[c][m + 1]);
         S[c][K - 1] = 0.f;
-        const int y = y0 + warp * 4 + c;
-        if (emit && y < A.ny && x < A.nx) {
-          const size_t idx = (size_t)z * plane + (size_t)y * A.nx + x;
+        if (emit && coff[c] >= 0) {
           const float blur = fmaxf(e, 0.f);  // img_ft[img_ft<0] = 0 (mv:5671)
           if (MODE == RL_PLAIN) {
-            A.out[idx] = blur;
+            oplane[coff[c]] = blur;
           } else if (MODE == RL_RATIO) {
             const float I = A.view_u16 ? u16_to_float(eRaw[c]) : eI[c];
             const float ratio = __fdiv_rn(I, blur + 1e-6f);
-            A.out[idx] = eW[c] > 1e-5f ? ratio : 0.f;
+            oplane[coff[c]] = eW[c] > 1e-5f ? ratio : 0.f;
           } else {
             const float o = blur * eW[c];
             const float corr = A.first ? o : eC[c] + o;
             if (A.last) {
               const float v = fminf(fmaxf(eI[c] * corr, 0.f), 65535.f);
-              A.est[A.est_off + idx] = v;
+              eplane[coff[c]] = v;
               local_sum += (double)v;
             } else {
-              A.out[idx] = corr;
+              oplane[coff[c]] = corr;
             }
           }
         }
       }
+    }
+    if (emit) {  // advance the epilogue planes
+      if (wplane) wplane += plane;
+      if (oplane) oplane += plane;
+      if (eplane) eplane += plane;
+      if (vplane) vplane += vstep;
     }
     // the y pass reads sB; sB is rewritten only after the next barrier, sA[buf] only by the plane after next
   }
