@@ -156,6 +156,25 @@ int mvf_rl_correct(const float* ratio, const int32_t* zmap, const int32_t dims[3
                    const float* weights, float* corr, int first, int last, float* est,
                    int64_t est_offset, double* sum_out, void* stream);
 
+/* ---- RL, general PSFs: cuFFT circular convolution with the reference's padding (mv:5647-5673) ------------
+ * For PSFs that are not outer products (oblique views).  The padded extents are the next 2^a3^b5^c7^d >=
+ * n + K - 1 per axis (the reference uses n + K + 1; the extra entries only hold zeros, the reflected tail and
+ * the wrap-around values are placed so that every output voxel sees the reference's inputs).  The caller owns
+ * all buffers: `real_buf` = prod(padded) floats, `cplx_buf` and each PSF spectrum = padded[0]*padded[1]*
+ * (padded[2]/2+1) float2, `workspace` = *workspace_bytes bytes (cuFFT work area).  mode: 0 = plain blur into
+ * `out`, 1 = ratio, 2 = correct; remaining arguments as for mvf_rl_ratio / mvf_rl_correct. */
+int mvf_rl_fft_padded_dims(const int32_t dims[3], const int32_t ksize[3], int32_t padded[3]);
+int mvf_rl_fft_plan_create(const int32_t dims[3], const int32_t ksize[3], void* workspace_or_null,
+                           size_t* workspace_bytes, void** plan_out);
+int mvf_rl_fft_plan_set_workspace(void* plan, void* workspace);
+int mvf_rl_fft_plan_destroy(void* plan);
+int mvf_rl_fft_psf_spectrum(void* plan, const float* psf, const int32_t ksize[3], float* real_buf,
+                            void* spectrum_out, void* stream);
+int mvf_rl_fft_blur(void* plan, const float* in, const int32_t* zmap, int zmap_radius, const int32_t ksize[3],
+                    const void* psf_spectrum, float* real_buf, void* cplx_buf, int mode,
+                    const void* view, int dtype, const float* weights, float* out, int first, int last,
+                    float* est, int64_t est_offset, double* sum_out, void* stream);
+
 /* ---- K3: DCT-entropy quality of blocks of a transformed view (determine_chunk_quality, mv:4496-4561) --
  * For every job (linear index into the nblocks grid) the size^3 block is read with stride `bin` from the
  * transformed view (zero beyond its extents), zero-filled like the reference, DCT-II(ortho)-transformed in

@@ -21,6 +21,8 @@ EXPORTS = (
     "mvf_affine_resample", "mvf_blend_weights", "mvf_fuse_weighted", "mvf_fuse_blend",
     "mvf_rl_padded_size", "mvf_rl_init_estimate", "mvf_rl_blur", "mvf_rl_ratio", "mvf_rl_correct",
     "mvf_dct_scratch_bytes", "mvf_dct_entropy",
+    "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
+    "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur",
 )
 MVF_RL_KMAX = 31
 
@@ -80,6 +82,14 @@ def _declare(lib):
     lib.mvf_rl_ratio.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mvf_rl_correct.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_fft_padded_dims.argtypes = [i32p, i32p, i32p]
+    lib.mvf_rl_fft_plan_create.argtypes = [i32p, i32p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    lib.mvf_rl_fft_plan_set_workspace.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mvf_rl_fft_plan_destroy.argtypes = [C.c_void_p]
+    lib.mvf_rl_fft_psf_spectrum.argtypes = [C.c_void_p, C.c_void_p, i32p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_fft_blur.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, i32p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_void_p]
     lib.mvf_dct_scratch_bytes.argtypes = [C.c_int, C.POINTER(C.c_int)]
     lib.mvf_dct_entropy.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int, C.c_int, i32p, C.c_void_p, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]

@@ -296,7 +296,6 @@ def fuse_block(tviews_block, weights, params, stack_properties, orig_stack_prope
     """Fuse one (V, 128+2d, ...) block (mv:3817-3916): drop views that are empty in the block, return the raw block
     of the only live view (or view 0) in the trivial cases, compute the block origin from the chunk location,
     call ``weights_func`` / ``fusion_func`` by keyword."""
-    import inspect
     max_vals = np.array([tview_block.max() for tview_block in tviews_block])
     inds = np.where(max_vals > 0)[0]
     if len(inds) == 0:
@@ -320,9 +319,9 @@ def fuse_block(tviews_block, weights, params, stack_properties, orig_stack_prope
     fusion_kwargs['stack_properties'] = block_stack_properties
     weights_kwargs['params'] = params
     fusion_kwargs['params'] = params
-    if 'orig_stack_propertiess' in dict(inspect.getmembers(weights_func.__code__))['co_varnames']:
+    if 'orig_stack_propertiess' in weights_func.__code__.co_varnames:
         weights_kwargs['orig_stack_propertiess'] = orig_stack_propertiess
-    if 'orig_stack_propertiess' in dict(inspect.getmembers(fusion_func.__code__))['co_varnames']:
+    if 'orig_stack_propertiess' in fusion_func.__code__.co_varnames:
         fusion_kwargs['orig_stack_propertiess'] = orig_stack_propertiess
     if weights is None and weights_func == get_weights_simple:
         weights = weights_func(**weights_kwargs)

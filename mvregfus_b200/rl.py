@@ -4,6 +4,7 @@ Host side: PSF construction helpers (separability test), the z plane maps that e
 handling, and the iteration loop.  The blurs and the fused pointwise algebra run in csrc/rl.cu.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -42,6 +43,54 @@ def make_dense_psf_struct(psf, device):
     s.ksize = _cabi.i32x3(psf.shape)
     s.dense = t.data_ptr()
     return s, t
+
+
+class FftBlur:
+    """cuFFT convolution state shared by the non-separable views of one RL problem: plan, work area, one real and
+    one half-spectrum buffer, and one PSF spectrum per view."""
+
+    def __init__(self, dims, ksize, device):
+        self.lib = _cabi.load()
+        self.dims, self.ksize = tuple(int(d) for d in dims), tuple(int(k) for k in ksize)
+        padded = (C.c_int32 * 3)()
+        _cabi.check(self.lib.mvf_rl_fft_padded_dims(_cabi.i32x3(self.dims), _cabi.i32x3(self.ksize), padded))
+        self.padded = tuple(int(x) for x in padded)
+        nbytes = C.c_size_t(0)
+        self.plan = C.c_void_p()
+        _cabi.check(self.lib.mvf_rl_fft_plan_create(_cabi.i32x3(self.dims), _cabi.i32x3(self.ksize), None,
+                                                    C.byref(nbytes), C.byref(self.plan)))
+        self.work = torch.empty(max(int(nbytes.value), 16), dtype=torch.uint8, device=device)
+        _cabi.check(self.lib.mvf_rl_fft_plan_set_workspace(self.plan, C.c_void_p(self.work.data_ptr())))
+        L = self.padded
+        self.real = torch.empty(L, dtype=torch.float32, device=device)
+        self.cplx = torch.empty((L[0], L[1], L[2] // 2 + 1, 2), dtype=torch.float32, device=device)
+        self.device = device
+
+    def spectrum(self, psf):
+        psf_d = torch.from_numpy(np.ascontiguousarray(psf, dtype=np.float32)).to(self.device)
+        L = self.padded
+        spec = torch.empty((L[0], L[1], L[2] // 2 + 1, 2), dtype=torch.float32, device=self.device)
+        _cabi.check(self.lib.mvf_rl_fft_psf_spectrum(self.plan, C.c_void_p(psf_d.data_ptr()), _cabi.i32x3(psf.shape),
+                                                     C.c_void_p(self.real.data_ptr()), C.c_void_p(spec.data_ptr()), _stream_ptr()))
+        return spec
+
+    def blur(self, src, zmap, rp, spec, mode, view=None, weights=None, out=None, first=0, last=0, est=None, est_off=0, sums=None):
+        _cabi.check(self.lib.mvf_rl_fft_blur(
+            self.plan, C.c_void_p(src.data_ptr()), C.c_void_p(zmap.data_ptr()), int(rp), _cabi.i32x3(self.ksize),
+            C.c_void_p(spec.data_ptr()), C.c_void_p(self.real.data_ptr()), C.c_void_p(self.cplx.data_ptr()), int(mode),
+            C.c_void_p(view.data_ptr()) if view is not None else None, dtype_code(view) if view is not None else 0,
+            C.c_void_p(weights.data_ptr()) if weights is not None else None,
+            C.c_void_p(out.data_ptr()) if out is not None else None, int(first), int(last),
+            C.c_void_p(est.data_ptr()) if est is not None else None, int(est_off),
+            C.c_void_p(sums.data_ptr()) if sums is not None else None, _stream_ptr()))
+
+    def __del__(self):
+        try:
+            if self.plan:
+                self.lib.mvf_rl_fft_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
 
 
 def make_psf_struct(factors):
@@ -86,17 +135,26 @@ class RLPlan:
         self.dims = tuple(int(s) for s in views[0].shape)
         dev = views[0].device
         self.psf_structs, self.zmaps, self.separable, self._keep = [], [], [], []
+        self.radii, self.spectra, self.fft = [], [], None
+        self.dense_mode = os.environ.get("MVF_RL_DENSE", "fft")  # 'fft' (cuFFT) or 'direct' (O(K^3) kernel)
         for p in psfs:
             f = factor_psf(p)
             self.separable.append(f is not None)
+            spec = None
             if f is not None:  # outer-product PSF (axis-aligned view): fused separable kernel
                 self.psf_structs.append(make_psf_struct(f))
                 ksz, rp = len(f[0]), padded_radius(f)
-            else:              # oblique view: dense PSF, direct convolution kernel
+            else:              # oblique view: dense PSF -> cuFFT convolution (or the direct kernel on request)
                 st, keep = make_dense_psf_struct(p, dev)
                 self.psf_structs.append(st)
                 self._keep.append(keep)
                 ksz, rp = int(np.asarray(p).shape[0]), (int(keep.shape[0]) - 1) // 2
+                if self.dense_mode == "fft":
+                    if self.fft is None:
+                        self.fft = FftBlur(self.dims, np.asarray(p).shape, dev)
+                    spec = self.fft.spectrum(np.asarray(p))
+            self.spectra.append(spec)
+            self.radii.append(rp)
             self.zmaps.append(torch.from_numpy(zmap_whole(self.dims[0], ksz, rp)).to(dev))
         self.est = torch.empty(self.dims, dtype=torch.float32, device=dev)
         self.ratio = torch.empty(self.dims, dtype=torch.float32, device=dev)
@@ -117,11 +175,18 @@ class RLPlan:
         st = _stream_ptr()
         self.sums[1:].zero_()
         for v in range(self.n):
+            last = v == self.n - 1
+            if self.spectra[v] is not None:  # cuFFT path
+                self.fft.blur(self.est, self.zmaps[v], self.radii[v], self.spectra[v], 1, view=self.views[v],
+                              weights=self.weights[v], out=self.ratio)
+                self.fft.blur(self.ratio, self.zmaps[v], self.radii[v], self.spectra[v], 2, weights=self.weights[v],
+                              out=self.corr, first=1 if v == 0 else 0, last=1 if last else 0, est=self.est,
+                              sums=self.sums[1:])
+                continue
             zm = C.c_void_p(self.zmaps[v].data_ptr())
             _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est.data_ptr()), zm, self._dims, C.byref(self.psf_structs[v]),
                                               C.c_void_p(self.views[v].data_ptr()), dtype_code(self.views[v]),
                                               C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.ratio.data_ptr()), st))
-            last = v == self.n - 1
             _cabi.check(self.lib.mvf_rl_correct(C.c_void_p(self.ratio.data_ptr()), zm, self._dims, C.byref(self.psf_structs[v]),
                                                 C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.corr.data_ptr()),
                                                 1 if v == 0 else 0, 1 if last else 0, C.c_void_p(self.est.data_ptr()), 0,

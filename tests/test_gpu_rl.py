@@ -79,9 +79,12 @@ def test_rl_delta_psf_fixed_point(cuda):
     assert np.max(np.abs(got - est)) <= 1e-3
 
 
-def test_rl_oblique_views_dense_psf(cuda):
-    """Views 7 degrees off axis: the PSF is not an outer product -> dense direct-convolution kernel."""
+@pytest.mark.parametrize("dense_mode", ["fft", "direct"])
+def test_rl_oblique_views_dense_psf(cuda, dense_mode, monkeypatch):
+    """Views 7 degrees off axis: the PSF is not an outer product -> cuFFT convolution (default) or the direct
+    O(K^3) kernel; both against the oracle's float64 FFT."""
     from mvregfus_b200 import fusion, rl, multiview as mv
+    monkeypatch.setenv("MVF_RL_DENSE", dense_mode)
     views, params, props, sp = small_case(shape=(40, 36, 44), nviews=2, dtype=np.uint16, seed=9, odd_extra_deg=7.0)
     tv = [O.transform_stack_dask_numpy(v, p, sp) for v, p in zip(views, params)]
     w = O.get_weights_simple(props, params, sp)

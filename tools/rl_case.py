@@ -11,6 +11,9 @@ w = [torch.full(shape, 1.0 / V, device="cuda") for _ in range(V)]
 k = np.exp(-0.5 * (np.arange(-9, 10) / 6.0) ** 2); kz = (k / k.sum()).astype(np.float32)
 k = np.exp(-0.5 * (np.arange(-9, 10) / 2.0) ** 2); kxy = (k / k.sum()).astype(np.float32)
 psf = kz[:, None, None] * kxy[None, :, None] * kxy[None, None, :]
+if os.environ.get("RL_OBLIQUE"):
+    from scipy import ndimage
+    psf = ndimage.rotate(psf, 7.0, axes=(0, 2), reshape=False, order=1).astype(np.float32); psf /= psf.sum()
 plan = rl.RLPlan(views, w, [psf] * V)
 plan.init_estimate(); plan.iterate(); torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
