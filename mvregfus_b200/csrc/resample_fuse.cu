@@ -254,12 +254,13 @@ __device__ __forceinline__ float lerp8(const float* p, int ox, int oy, int oz, f
 // Trilinear value at brick-relative coordinate rel (float64), scipy 'constant' rule: 0 when the view
 // coordinate is outside [0, n-1] (ni_interpolation.c NI_GeometricTransform, mode constant).
 template <bool INTERIOR>
-__device__ __forceinline__ float gather_scipy(const float* sm, int px, int pz, const double rel[3], const double lo[3], const double hi[3]) {
+__device__ __forceinline__ float gather_scipy(const float* sm, const TileView& t, const double u[3], const double hi[3]) {
   int r[3], neg[3];
   float w[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) split_nearest(rel[d], r[d], w[d], neg[d]);
-  const float* p = sm + r[0] * pz + r[1] * px + r[2];
+  for (int d = 0; d < 3; ++d) split_nearest(u[d], r[d], w[d], neg[d]);
+  const int px = t.px, pz = t.pz;
+  const float* p = sm + (r[0] - t.b0[0]) * pz + (r[1] - t.b0[1]) * px + (r[2] - t.b0[2]);
   const int ox = 1 | neg[2];
   const int oy = (px ^ neg[1]) - neg[1];
   const int oz = (pz ^ neg[0]) - neg[0];
@@ -267,7 +268,7 @@ __device__ __forceinline__ float gather_scipy(const float* sm, int px, int pz, c
   if (!INTERIOR) {
     bool inside = true;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) inside = inside && (rel[d] >= lo[d]) && (rel[d] <= hi[d]);
+    for (int d = 0; d < 3; ++d) inside = inside && (u[d] >= 0.0) && (u[d] <= hi[d]);
     val = inside ? val : 0.f;
   }
   return val;
@@ -384,15 +385,17 @@ __device__ __forceinline__ float field_lerp_1d(const float* f, int i, float t) {
   return fmaf(b - a, t, a);
 }
 
-__device__ __forceinline__ void ramp_coord(float cf, float cm, int ci, int k, int& i, float& t) {
-  float c = fmaf((float)k, cm, cf);
-  float y = __fadd_rd(c, MAGIC32);
-  t = c - (y - MAGIC32);
-  i = ci + (__float_as_int(y) - 0x4B400000);
-  i = max(0, min(i, MVF_SIG_N - 2));  // rounding guard at the bbox limits
+// floor and fraction of a float64 field coordinate with two DADDs (round-down magic add) and one F2F
+__device__ __forceinline__ void ramp_coord(double c, int& i, float& t) {
+  const double y = __dadd_rd(c, MAGIC64);
+  i = __double2loint(y);
+  t = (float)(c - (y - MAGIC64));
 }
 
 // Raw (un-normalised) blending weights of the TZ voxels of a thread (fused index (gz+k, gy, gx)) for one view.
+// Field coordinates come from the closed form c_d(z) = wm_d0 * z + (wm_d1 * y + wm_d2 * x + wo_d) in float64, so
+// a voxel's weight does not depend on the tile/slab decomposition; the tile class only selects how much of the
+// (identical) arithmetic can be skipped.
 __device__ __forceinline__ void column_blend(const KView& kv, int cls, int wdims, int gz, int gy, int gx, float (&w)[TZ]) {
   if (cls == WT_ZERO || cls == WT_ONE) {
     const float c = cls == WT_ONE ? 1.f : 0.f;
@@ -401,28 +404,22 @@ __device__ __forceinline__ void column_blend(const KView& kv, int cls, int wdims
     return;
   }
   double cb[3];
-  affine_base(kv.wm, kv.wo, gz, gy, gx, cb);
-  if (cls == WT_RAMP) {
-    // float32 steps on a float64 base: |error| < 1e-6 field voxels, i.e. < 3e-7 in the weight
-    int ci[3];
-    float cf[3], cm[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      ci[d] = __double2int_rd(cb[d]);
-      cf[d] = (float)(cb[d] - (double)ci[d]);
-      cm[d] = (float)kv.wm[d * 3 + 0];
-    }
-    if (wdims == 1 || wdims == 2 || wdims == 4) {  // one active axis (CTA-uniform)
+  for (int d = 0; d < 3; ++d) cb[d] = fma(kv.wm[d * 3 + 1], (double)gy, fma(kv.wm[d * 3 + 2], (double)gx, kv.wo[d]));
+  double zd = (double)gz;
+  if (cls == WT_RAMP) {
+    if (wdims == 1 || wdims == 2 || wdims == 4) {  // one active axis (CTA-uniform): 1-D lerp of its profile
       const int d = wdims == 1 ? 0 : (wdims == 2 ? 1 : 2);
       const float* f = kv.prof + d * MVF_SIG_N;
-      const float cfd = cf[d], cmd = cm[d];
-      const int cid = ci[d];
+      const double step = kv.wm[d * 3 + 0], c0 = cb[d];
 #pragma unroll
       for (int k = 0; k < TZ; ++k) {
         int i;
         float t;
-        ramp_coord(cfd, cmd, cid, k, i, t);
+        ramp_coord(fma(step, zd, c0), i, t);
+        i = max(0, min(i, MVF_SIG_N - 2));  // rounding guard at the bbox limits
         w[k] = field_lerp_1d(f, i, t);
+        zd += 1.0;
       }
       return;
     }
@@ -431,20 +428,16 @@ __device__ __forceinline__ void column_blend(const KView& kv, int cls, int wdims
       int i0[3];
       float t[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) ramp_coord(cf[d], cm[d], ci[d], k, i0[d], t[d]);
+      for (int d = 0; d < 3; ++d) {
+        ramp_coord(fma(kv.wm[d * 3 + 0], zd, cb[d]), i0[d], t[d]);
+        i0[d] = max(0, min(i0[d], MVF_SIG_N - 2));
+      }
       w[k] = field_lerp(kv.prof, i0[0], i0[1], i0[2], i0[0] + 1, i0[1] + 1, i0[2] + 1, t[0], t[1], t[2]);
+      zd += 1.0;
     }
   } else {
-    // tile touches the rim of the field: the ITK inside test [-0.5, N-0.5) is evaluated exactly in float64, the
-    // sample itself with the float32 index arithmetic above (neighbours clamped to the edge)
-    int ci[3];
-    float cf[3], cm[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      ci[d] = __double2int_rd(cb[d]);
-      cf[d] = (float)(cb[d] - (double)ci[d]);
-      cm[d] = (float)kv.wm[d * 3 + 0];
-    }
+    // tile touches the rim of the field: ITK inside test [-0.5, N-0.5) on the float64 coordinate, neighbours
+    // clamped to the edge
 #pragma unroll
     for (int k = 0; k < TZ; ++k) {
       int i0[3], i1[3];
@@ -452,12 +445,11 @@ __device__ __forceinline__ void column_blend(const KView& kv, int cls, int wdims
       bool inside = true;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const double c64 = fma((double)k, kv.wm[d * 3 + 0], cb[d]);
+        const double c64 = fma(kv.wm[d * 3 + 0], zd, cb[d]);
         inside = inside && (c64 >= -0.5) && (c64 < (double)MVF_SIG_N - 0.5);
-        float c = fmaf((float)k, cm[d], cf[d]);
-        float y = __fadd_rd(c, MAGIC32);
-        float tt = c - (y - MAGIC32);
-        int i = ci[d] + (__float_as_int(y) - 0x4B400000);
+        int i;
+        float tt;
+        ramp_coord(c64, i, tt);
         tt = i < 0 ? 0.f : tt;
         i0[d] = max(0, min(i, MVF_SIG_N - 1));
         i1[d] = min(i0[d] + 1, MVF_SIG_N - 1);
@@ -465,7 +457,60 @@ __device__ __forceinline__ void column_blend(const KView& kv, int cls, int wdims
       }
       float wv = field_lerp(kv.prof, i0[0], i0[1], i0[2], i1[0], i1[1], i1[2], t[0], t[1], t[2]);
       w[k] = inside ? wv : 0.f;
+      zd += 1.0;
     }
+  }
+}
+
+// ITK clamp of one continuous index: base index, upper neighbour, lerp weight, inside flag
+__device__ __forceinline__ void itk_axis(double c, int n, int& i0, int& i1, float& t, bool& inside) {
+  inside = (c >= -0.5) && (c < (double)n - 0.5);
+  int i = __double2int_rd(c);
+  double fr = c - (double)i;
+  if (i < 0) { i = 0; fr = 0.0; }
+  if (i >= n - 1) { i = n - 1; fr = 0.0; }
+  i0 = i;
+  i1 = min(i + 1, n - 1);
+  t = (float)fr;
+}
+
+// ITK-linear samples of the coarse DCT weight grid (mv:4304-4311) at the TZ voxels of a column.  The coarse
+// index changes by 1/(size*bin) per voxel, so the (y,x) bilinear part is evaluated once per coarse z plane the
+// column touches (at most 3) and only the final z lerp runs per voxel - same nesting order (x, y, z) as ITK.
+__device__ __forceinline__ void column_coarse(const KView& kv, int gz, int gy, int gx, float (&cw)[TZ]) {
+  if (kv.wmode != MVF_W_BLEND_DCT) {
+#pragma unroll
+    for (int k = 0; k < TZ; ++k) cw[k] = 0.f;
+    return;
+  }
+  int y0, y1, x0, x1;
+  float ty, tx;
+  bool in_y, in_x;
+  itk_axis(fma(kv.cs[1], (double)gy, kv.co[1]), kv.cd[1], y0, y1, ty, in_y);
+  itk_axis(fma(kv.cs[2], (double)gx, kv.co[2]), kv.cd[2], x0, x1, tx, in_x);
+  const double cz0 = fma(kv.cs[0], (double)gz, kv.co[0]);
+  int zb = max(0, min(__double2int_rd(cz0), kv.cd[0] - 1));
+  const float* g = kv.cgrid;
+  const int sy = kv.cd[2], sz = kv.cd[1] * kv.cd[2];
+  float plane[4];  // cs[0] <= 1/4 (DCT blocks are >= 4 voxels, mv:3949): a column of TZ=8 voxels spans <= 3 planes + 1
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* q = g + min(zb + j, kv.cd[0] - 1) * sz;
+    float a = __ldg(q + y0 * sy + x0), b = __ldg(q + y0 * sy + x1);
+    float c = __ldg(q + y1 * sy + x0), d = __ldg(q + y1 * sy + x1);
+    float r0 = fmaf(b - a, tx, a), r1 = fmaf(d - c, tx, c);
+    plane[j] = fmaf(r1 - r0, ty, r0);
+  }
+#pragma unroll
+  for (int k = 0; k < TZ; ++k) {
+    int z0i, z1i;
+    float tz;
+    bool in_z;
+    itk_axis(fma(kv.cs[0], (double)(gz + k), kv.co[0]), kv.cd[0], z0i, z1i, tz, in_z);
+    const int a = z0i - zb, b = z1i - zb;
+    const float va = a <= 0 ? plane[0] : (a == 1 ? plane[1] : (a == 2 ? plane[2] : plane[3]));
+    const float vb = b <= 0 ? plane[0] : (b == 1 ? plane[1] : (b == 2 ? plane[2] : plane[3]));
+    cw[k] = (in_z && in_y && in_x) ? fmaf(vb - va, tz, va) : 0.f;
   }
 }
 
@@ -497,14 +542,12 @@ __device__ __forceinline__ void column_weights(const KArgs& A, const TileView* t
     for (int k = 0; k < TZ; ++k) wsum2[k] = 0.f;
     for (int v = 0; v < A.nviews; ++v) {
       const KView& kv = A.v[v];
+      float cw[TZ];
+      column_coarse(kv, gz, gy, gx, cw);
 #pragma unroll
       for (int k = 0; k < TZ; ++k) {
         float wn = __fdiv_rn(wsm[(v * TZ + k) * NT + tid], wsum[k]);
-        float cw = 0.f;
-        if (wn != 0.f && kv.wmode == MVF_W_BLEND_DCT)
-          cw = coarse_sample(kv, fma(kv.cs[0], (double)(gz + k), kv.co[0]), fma(kv.cs[1], (double)gy, kv.co[1]),
-                             fma(kv.cs[2], (double)gx, kv.co[2]));
-        wn = cw * wn;
+        wn = (wn != 0.f && kv.wmode == MVF_W_BLEND_DCT) ? cw[k] * wn : 0.f * wn;
         wsm[(v * TZ + k) * NT + tid] = wn;
         wsum2[k] += wn;
       }
@@ -519,20 +562,20 @@ __device__ __forceinline__ void column_weights(const KArgs& A, const TileView* t
 template <bool INTERIOR, typename Sink>
 __device__ __forceinline__ void column_gather(const float* sm, const TileView& t, const KView& kv, int gz, int gy, int gx,
                                               Sink sink) {
-  double rel[3], lo[3], hi[3];
-  affine_base(kv.m, kv.o, gz, gy, gx, rel);
+  // u_d(z) = m_d0 * z + (m_d1 * y + m_d2 * x + o_d): one float64 FMA per axis and voxel on an exact z, so a voxel's
+  // coordinate (hence its value) is the same whatever tile, chunk or z-slab it is computed in.
+  double base[3], hi[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    rel[d] -= (double)t.b0[d];
-    lo[d] = -(double)t.b0[d];
-    hi[d] = (double)(kv.n[d] - 1 - t.b0[d]);
+    base[d] = fma(kv.m[d * 3 + 1], (double)gy, fma(kv.m[d * 3 + 2], (double)gx, kv.o[d]));
+    hi[d] = (double)(kv.n[d] - 1);
   }
-  const int px = t.px, pz = t.pz;
+  double zd = (double)gz;
 #pragma unroll
   for (int k = 0; k < TZ; ++k) {
-    sink(k, gather_scipy<INTERIOR>(sm, px, pz, rel, lo, hi));
-#pragma unroll
-    for (int d = 0; d < 3; ++d) rel[d] += kv.m[d * 3 + 0];
+    const double u[3] = {fma(kv.m[0], zd, base[0]), fma(kv.m[3], zd, base[1]), fma(kv.m[6], zd, base[2])};
+    sink(k, gather_scipy<INTERIOR>(sm, t, u, hi));
+    zd += 1.0;
   }
 }
 
@@ -638,15 +681,16 @@ __global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ KA
       if (t.interior) column_gather<true>(sm, t, kv, gz, gy, gx, sink);
       else column_gather<false>(sm, t, kv, gz, gy, gx, sink);
     } else {
-      double rel[3];
-      affine_base(kv.m, kv.o, gz, gy, gx, rel);
+      double base[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) rel[d] -= (double)t.b0[d];
+      for (int d = 0; d < 3; ++d) base[d] = fma(kv.m[d * 3 + 1], (double)gy, fma(kv.m[d * 3 + 2], (double)gx, kv.o[d]));
+      double zd = (double)gz;
 #pragma unroll 1
       for (int k = 0; k < TZ; ++k) {
+        const double rel[3] = {fma(kv.m[0], zd, base[0]) - (double)t.b0[0], fma(kv.m[3], zd, base[1]) - (double)t.b0[1],
+                               fma(kv.m[6], zd, base[2]) - (double)t.b0[2]};
         val[k] = gather_itk(sm, t, kv, rel);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) rel[d] += kv.m[d * 3 + 0];
+        zd += 1.0;
       }
     }
   }
