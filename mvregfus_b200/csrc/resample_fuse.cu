@@ -210,7 +210,23 @@ __device__ __forceinline__ void commit_brick(const KView& kv, const TileView& t,
       const unsigned i = threadIdx.x + u * NT;
       if (i < t.total) store_chunk<T>(t, i, q[u], sm);
     }
-    for (unsigned i = threadIdx.x + PF * NT; i < t.total; i += NT) store_chunk<T>(t, i, load_chunk<T>(kv, t, i), sm);
+    // the rest of the brick: batches of 4 chunks per thread, all loads of a batch issued before its first store
+    // (the registers are free here: nothing of the gather is live between the two barriers)
+    constexpr int U = 4;
+    for (unsigned i0 = threadIdx.x + PF * NT; i0 < t.total; i0 += NT * U) {
+      uint4 r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned i = i0 + u * NT;
+        r[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < t.total) r[u] = load_chunk<T>(kv, t, i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned i = i0 + u * NT;
+        if (i < t.total) store_chunk<T>(t, i, r[u], sm);
+      }
+    }
   } else {
     const T* __restrict__ src = reinterpret_cast<const T*>(kv.data);
     for (unsigned i = threadIdx.x; i < t.total; i += NT) {
