@@ -21,7 +21,7 @@ __all__ = [
     "calc_stack_properties_from_volume", "calc_stack_properties_from_views_and_params",
     "get_psf", "fuse_LR_with_weights_np",
     "get_dct_options", "determine_chunk_quality", "get_weights_dct_dask", "get_weights_dct",
-    "fuse_block", "fuse_blockwise", "fuse_blockwise_arrays",
+    "fuse_block", "fuse_blockwise", "fuse_blockwise_arrays", "transform_view_dask_and_save_chunked",
 ]
 
 
@@ -135,6 +135,20 @@ def affine_transform_dask(input, matrix, offset=0.0, output_shape=None, output_c
     src = fusion.to_device(input)
     res = fusion.affine_resample(src, matrix, offset, [int(s) for s in output_shape], (0, 0, 0), rule="scipy")
     return _maybe_dask(res.cpu().numpy(), output_chunks)
+
+
+def transform_view_dask_and_save_chunked(fn, view, params, iview, stack_properties, chunksize=128):
+    """Resample view ``iview`` into the fused frame and store it as HDF5 dataset 'Data' in ``fn`` (mv:1746-1769).
+    File formats stay the reference's business: this needs h5py."""
+    try:
+        import h5py
+    except ImportError as e:
+        raise Exception("transform_view_dask_and_save_chunked writes HDF5 and needs h5py (%s)" % e)
+    res = transform_stack_dask_numpy(view, params[iview], stack_properties=stack_properties, interp='linear',
+                                     chunksize=chunksize)
+    with h5py.File(fn, 'w') as f:
+        f.create_dataset('Data', data=np.asarray(res))
+    return fn
 
 
 def _maybe_dask(arr, chunks):

@@ -73,6 +73,7 @@ REFERENCE_SIGNATURES = {
     "fuse_block": "(tviews_block, weights, params, stack_properties, orig_stack_propertiess, array_info, weights_func, fusion_func, weights_kwargs, fusion_kwargs, block_info=None)",
     "fuse_blockwise": "(fn, fns_tview, params, stack_properties, orig_stack_propertiess, fusion_block_overlap=None, weights_func=None, fusion_func=None, weights_kwargs=None, fusion_kwargs=None)",
     "calc_stack_properties_from_views_and_params": "(views_props, params, spacing=None, mode='sample')",
+    "transform_view_dask_and_save_chunked": "(fn, view, params, iview, stack_properties, chunksize=128)",
 }
 
 
