@@ -32,7 +32,7 @@ extern "C" {
 #define MVF_ABI_VERSION 1
 #define MVF_MAX_VIEWS 8      /* views fused in one pass (register-resident weights)           */
 #define MVF_SIG_N 200        /* samples per axis of the blending field, mv:3566               */
-#define MVF_RL_KMAX 31       /* longest separable PSF factor handled by the RL kernels         */
+#define MVF_RL_KMAX 43       /* longest PSF factor handled by the RL convolution kernels        */
 
 enum { MVF_U16 = 0, MVF_F32 = 1 };                 /* voxel dtypes                            */
 enum { MVF_RULE_SCIPY = 0, MVF_RULE_ITK = 1 };     /* boundary rule of order-1 resampling      */
@@ -133,7 +133,7 @@ typedef struct mvf_rl_psf {
   const float* dense;
 } mvf_rl_psf;
 
-/* kernel template size used for a PSF whose longest factor has k taps (7, 13, 19, 25 or 31; -1 if k > 31) */
+/* kernel template size used for a PSF whose longest factor has k taps (7, 13, ..., 43 in steps of 6; -1 if k > 43) */
 int mvf_rl_padded_size(int k);
 
 /* estimate = sum_v w_v * I_v (float32, views added in order; mv:5629); *sum_out += sum(estimate). */

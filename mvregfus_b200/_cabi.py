@@ -24,7 +24,7 @@ EXPORTS = (
     "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
     "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur",
 )
-MVF_RL_KMAX = 31
+MVF_RL_KMAX = 43
 
 
 class MvfView(C.Structure):
@@ -50,7 +50,7 @@ class MvfView(C.Structure):
 
 class MvfRlPsf(C.Structure):
     """struct mvf_rl_psf: separable PSF factors (true-convolution taps)."""
-    _fields_ = [("kz", C.c_float * 31), ("ky", C.c_float * 31), ("kx", C.c_float * 31), ("ksize", C.c_int32 * 3),
+    _fields_ = [("kz", C.c_float * 43), ("ky", C.c_float * 43), ("kx", C.c_float * 43), ("ksize", C.c_int32 * 3),
                 ("dense", C.c_void_p)]
 
 

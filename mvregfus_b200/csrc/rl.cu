@@ -16,7 +16,9 @@
 
 namespace mvf {
 
-constexpr int RL_TX = 32, RL_TY = 32, RL_NT = 256, RL_CPT = 4;  // 4 (y) columns per thread
+constexpr int RL_TX = 32, RL_TY = 32;
+// threads own CPT consecutive y rows of one x column: CPT = 4 (256 threads) for PSFs up to 19 taps, CPT = 2
+// (512 threads) beyond, so that the CPT x K shift register of partial sums still fits the register file
 constexpr int RL_KMAX = MVF_RL_KMAX;
 
 enum { RL_PLAIN = 0, RL_RATIO = 1, RL_CORRECT = 2 };
@@ -59,8 +61,9 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int K, int MODE>
-__global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant__ RLArgs A) {
+template <int K, int MODE, int RL_CPT>
+__global__ void __launch_bounds__(32 * (RL_TY / RL_CPT), RL_CPT == 4 ? 2 : 1) rl_blur_kernel(const __grid_constant__ RLArgs A) {
+  constexpr int RL_NT = 32 * (RL_TY / RL_CPT);
   constexpr int R = (K - 1) / 2;
   constexpr int LEAD = (R + 3) & ~3;            // x halo rounded up to whole 16-byte chunks
   constexpr int AY = RL_TY + 2 * R, AX = RL_TX + 2 * LEAD;
@@ -70,11 +73,14 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
   constexpr int NV = (AY * CPR + RL_NT - 1) / RL_NT;   // vector copies per thread and plane
   constexpr int NS = (AY * AX + RL_NT - 1) / RL_NT;    // scalar copies (tiles touching the x border / unaligned rows)
   constexpr int WIN = 4 + 2 * LEAD;             // x-pass register window (whole chunks)
-  __shared__ __align__(16) float sA[2][AY * PA];  // double buffered: plane t+1 streams in while plane t is filtered
-  __shared__ float sB[AY * PB];
-  __shared__ int sRowOff[AY];      // ext-mapped source row offsets (y * nx)
-  __shared__ int sCol[AX];         // ext-mapped source columns
-  extern __shared__ int sZ[];      // plane map of this CTA's z range
+  // dynamic shared memory: two plane tiles (plane t+1 streams in while plane t is filtered), the x-pass output,
+  // the ext-mapped row offsets / columns of the tile and the plane map of this CTA's z range
+  extern __shared__ __align__(16) unsigned char rl_smem[];
+  float (*sA)[AY * PA] = reinterpret_cast<float (*)[AY * PA]>(rl_smem);
+  float* sB = reinterpret_cast<float*>(rl_smem) + 2 * AY * PA;
+  int* sRowOff = reinterpret_cast<int*>(sB + AY * PB);
+  int* sCol = sRowOff + AY;
+  int* sZ = sCol + AX;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.x * RL_TX, y0 = blockIdx.y * RL_TY;
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
   int coff[RL_CPT];
 #pragma unroll
   for (int c = 0; c < RL_CPT; ++c) {
-    const int y = y0 + warp * 4 + c;
+    const int y = y0 + warp * RL_CPT + c;
     coff[c] = (y < A.ny && x < A.nx) ? y * A.nx + x : -1;
   }
   const float* __restrict__ wplane = A.weights ? A.weights + (size_t)zo0 * plane : nullptr;
@@ -193,11 +199,13 @@ __global__ void __launch_bounds__(RL_NT, 2) rl_blur_kernel(const __grid_constant
     __syncthreads();
     // ---- y pass: thread (lane = x, warp = strip of 4 y), then the z shift register
     {
-      const float* b = sB + (warp * 4) * PB + lane;
-      float win[4 + 2 * R];
+      const float* b = sB + (warp * RL_CPT) * PB + lane;
+      float win[RL_CPT + 2 * R];
 #pragma unroll
-      for (int j = 0; j < 4 + 2 * R; ++j) win[j] = b[j * PB];
-      float p[RL_CPT] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < RL_CPT + 2 * R; ++j) win[j] = b[j * PB];
+      float p[RL_CPT];
+#pragma unroll
+      for (int c = 0; c < RL_CPT; ++c) p[c] = 0.f;
 #pragma unroll
       for (int j = 0; j < K; ++j) {
         const float kj = A.ky[j];
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(256) rl_init_kernel(const __grid_constant__ RL
 }
 
 static int padded_size(int k) {
-  const int sizes[] = {7, 13, 19, 25, 31};
+  const int sizes[] = {7, 13, 19, 25, 31, 37, 43};
   for (int s : sizes)
     if (k <= s) return s;
   return -1;
@@ -354,8 +362,23 @@ static int launch_rl_direct(int kp, const RLArgs& A, cudaStream_t st) {
     case 19: rl_direct_kernel<19, MODE><<<grid, 256, 0, st>>>(A); break;
     case 25: rl_direct_kernel<25, MODE><<<grid, 256, 0, st>>>(A); break;
     case 31: rl_direct_kernel<31, MODE><<<grid, 256, 0, st>>>(A); break;
-    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "PSF longer than 31 taps");
+    case 37: rl_direct_kernel<37, MODE><<<grid, 256, 0, st>>>(A); break;
+    case 43: rl_direct_kernel<43, MODE><<<grid, 256, 0, st>>>(A); break;
+    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "PSF longer than 43 taps");
   }
+  MVF_LAUNCHED();
+  return MVF_OK;
+}
+
+template <int K, int MODE, int CPT>
+static int launch_rl_k(const RLArgs& A, cudaStream_t st) {
+  constexpr int R = (K - 1) / 2, LEAD = (R + 3) & ~3;
+  constexpr int AY = RL_TY + 2 * R, AX = RL_TX + 2 * LEAD;
+  dim3 grid((A.nx + RL_TX - 1) / RL_TX, (A.ny + RL_TY - 1) / RL_TY, (A.nz + A.zchunk - 1) / A.zchunk);
+  const size_t smem = (size_t)(2 * AY * AX + AY * (RL_TX + 1)) * sizeof(float) + (size_t)(AY + AX + A.zchunk + K - 1) * sizeof(int);
+  auto kern = rl_blur_kernel<K, MODE, CPT>;
+  MVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, 32 * (RL_TY / CPT), smem, st>>>(A);
   MVF_LAUNCHED();
   return MVF_OK;
 }
@@ -363,18 +386,16 @@ static int launch_rl_direct(int kp, const RLArgs& A, cudaStream_t st) {
 template <int MODE>
 static int launch_rl(int kp, const RLArgs& A, cudaStream_t st) {
   if (A.dense) return launch_rl_direct<MODE>(kp, A, st);
-  dim3 grid((A.nx + RL_TX - 1) / RL_TX, (A.ny + RL_TY - 1) / RL_TY, (A.nz + A.zchunk - 1) / A.zchunk);
-  const size_t zs = (size_t)(A.zchunk + kp - 1) * sizeof(int);
   switch (kp) {
-    case 7: rl_blur_kernel<7, MODE><<<grid, RL_NT, zs, st>>>(A); break;
-    case 13: rl_blur_kernel<13, MODE><<<grid, RL_NT, zs, st>>>(A); break;
-    case 19: rl_blur_kernel<19, MODE><<<grid, RL_NT, zs, st>>>(A); break;
-    case 25: rl_blur_kernel<25, MODE><<<grid, RL_NT, zs, st>>>(A); break;
-    case 31: rl_blur_kernel<31, MODE><<<grid, RL_NT, zs, st>>>(A); break;
-    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 31 taps");
+    case 7: return launch_rl_k<7, MODE, 4>(A, st);
+    case 13: return launch_rl_k<13, MODE, 4>(A, st);
+    case 19: return launch_rl_k<19, MODE, 4>(A, st);
+    case 25: return launch_rl_k<25, MODE, 2>(A, st);
+    case 31: return launch_rl_k<31, MODE, 2>(A, st);
+    case 37: return launch_rl_k<37, MODE, 2>(A, st);
+    case 43: return launch_rl_k<43, MODE, 2>(A, st);
+    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 43 taps");
   }
-  MVF_LAUNCHED();
-  return MVF_OK;
 }
 
 static int fill_rl(RLArgs& A, const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf, int* kp) {
@@ -383,7 +404,7 @@ static int fill_rl(RLArgs& A, const float* in, const int32_t* zmap, const int32_
   int kmax = 0;
   for (int d = 0; d < 3; ++d) {
     if (psf->ksize[d] < 1 || psf->ksize[d] > RL_KMAX || !(psf->ksize[d] & 1))
-      return fail(MVF_ERR_INVALID, "%s%s", "rl: PSF sizes must be odd and <= 31");
+      return fail(MVF_ERR_INVALID, "%s%s", "rl: PSF sizes must be odd and <= 43");
     if (dims[d] < psf->ksize[d] + 3)
       return fail(MVF_ERR_UNSUPPORTED, "%s%s", "rl: volume extent smaller than PSF size + 3 (the reference's reflect padding needs it)");
     kmax = psf->ksize[d] > kmax ? psf->ksize[d] : kmax;

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib.mvf_abi_version.restype = ctypes.c_int
     assert lib.mvf_abi_version() == 1
     lib.mvf_rl_padded_size.restype = ctypes.c_int
-    assert [lib.mvf_rl_padded_size(k) for k in (1, 7, 9, 19, 21, 31, 33)] == [7, 7, 13, 19, 25, 31, -1]
+    assert [lib.mvf_rl_padded_size(k) for k in (1, 7, 9, 19, 21, 31, 33, 43, 45)] == [7, 7, 13, 19, 25, 31, 37, 43, -1]
 
 
 def test_struct_layout_matches_header(tmp_path):

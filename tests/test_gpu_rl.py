@@ -16,12 +16,12 @@ def _axis_case(shape=(48, 40, 56), nviews=2, seed=5):
     return tv, w, params, sp
 
 
-@pytest.mark.parametrize("ksize", [(7, 7, 7), (19, 19, 19), (5, 9, 13)])
+@pytest.mark.parametrize("ksize", [(7, 7, 7), (19, 19, 19), (5, 9, 13), (25, 25, 25), (37, 37, 37), (9, 31, 43)])
 def test_blur_matches_closed_form(cuda, ksize):
     import torch
     from mvregfus_b200 import rl
     rng = np.random.default_rng(1)
-    x = rng.random((40, 45, 70)).astype(np.float32) * 100
+    x = rng.random((48, 50, 70)).astype(np.float32) * 100
     f = [np.exp(-0.5 * ((np.arange(k) - k // 2) / (0.15 * k + 0.5)) ** 2).astype(np.float32) for k in ksize]
     f = [(a / a.sum()).astype(np.float32) for a in f]
     f[0][0] *= 1.3  # asymmetric taps: catches a flipped kernel
