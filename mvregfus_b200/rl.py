@@ -242,10 +242,13 @@ class SlabRLPlan:
         if len(shapes) != 1:
             raise ValueError("all views must share one PSF shape")
         kz = next(iter(shapes))[0]
-        self.psf_structs, self._keep = [], []
+        self.psf_structs, self._keep, self.spectra = [], [], []
+        self.fft = None
+        dense_mode = os.environ.get("MVF_RL_DENSE", "fft")
         rp = None
         for p in psfs:
             f = factor_psf(p)
+            spec = None
             if f is not None:
                 self.psf_structs.append(make_psf_struct(f))
                 r = padded_radius(f)
@@ -254,6 +257,11 @@ class SlabRLPlan:
                 self.psf_structs.append(st)
                 self._keep.append(keep)
                 r = (int(keep.shape[0]) - 1) // 2
+                if dense_mode == "fft":
+                    if self.fft is None:
+                        self.fft = FftBlur((nzl, ny, nx), np.asarray(p).shape, dev)
+                    spec = self.fft.spectrum(np.asarray(p))
+            self.spectra.append(spec)
             rp = r if rp is None else rp
             if r != rp:
                 raise ValueError("PSFs need one common padded size")
@@ -281,6 +289,10 @@ class SlabRLPlan:
 
     def step_ratio(self, v):
         """R_v = I_v / (blur(est) + 1e-6) * mask, read from the halo-padded estimate."""
+        if self.spectra[v] is not None:
+            self.fft.blur(self.est_pad, self.zmap, self.rp, self.spectra[v], 1, view=self.views[v],
+                          weights=self.weights[v], out=self.ratio)
+            return
         _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
                                           C.byref(self.psf_structs[v]), C.c_void_p(self.views[v].data_ptr()),
                                           dtype_code(self.views[v]), C.c_void_p(self.weights[v].data_ptr()),
@@ -289,6 +301,11 @@ class SlabRLPlan:
     def step_correct(self, v):
         """C (+)= blur(R_v) * w_v; the last view applies the multiplicative update to the estimate."""
         last = v == self.n - 1
+        if self.spectra[v] is not None:
+            self.fft.blur(self.ratio_pad, self.zmap, self.rp, self.spectra[v], 2, weights=self.weights[v], out=self.corr,
+                          first=1 if v == 0 else 0, last=1 if last else 0, est=self.est_pad, est_off=self._est_off,
+                          sums=self.sums[1:])
+            return
         _cabi.check(self.lib.mvf_rl_correct(C.c_void_p(self.ratio_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
                                             C.byref(self.psf_structs[v]), C.c_void_p(self.weights[v].data_ptr()),
                                             C.c_void_p(self.corr.data_ptr()), 1 if v == 0 else 0, 1 if last else 0,
