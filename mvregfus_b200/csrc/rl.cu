@@ -16,6 +16,9 @@
 
 namespace mvf {
 
+#ifndef MVF_RL_XS
+#define MVF_RL_XS 4
+#endif
 constexpr int RL_TX = 32, RL_TY = 32;
 // threads own CPT consecutive y rows of one x column: CPT = 4 (256 threads) for PSFs up to 19 taps, CPT = 2
 // (512 threads) beyond, so that the CPT x K shift register of partial sums still fits the register file
@@ -67,12 +70,15 @@ __global__ void __launch_bounds__(32 * (RL_TY / RL_CPT), RL_CPT == 4 ? 2 : 1) rl
   constexpr int R = (K - 1) / 2;
   constexpr int LEAD = (R + 3) & ~3;            // x halo rounded up to whole 16-byte chunks
   constexpr int AY = RL_TY + 2 * R, AX = RL_TX + 2 * LEAD;
-  constexpr int PA = AX;                        // multiple of 4: rows are 16-byte aligned for cp.async / LDS.128
+  constexpr int XS = MVF_RL_XS;                 // outputs per x-pass work item (4 or 8)
+  // multiple of 4 (rows 16-byte aligned for cp.async / LDS.128); with 8-wide strips two tile rows share a quarter
+  // warp, so the pitch is made = 4 (mod 8) words to keep their LDS.128 on disjoint banks
+  constexpr int PA = (XS == 8 && (AX % 8) == 0) ? AX + 4 : AX;
   constexpr int PB = RL_TX + 1;
   constexpr int CPR = AX / 4;                   // 16-byte chunks per tile row
   constexpr int NV = (AY * CPR + RL_NT - 1) / RL_NT;   // vector copies per thread and plane
   constexpr int NS = (AY * AX + RL_NT - 1) / RL_NT;    // scalar copies (tiles touching the x border / unaligned rows)
-  constexpr int WIN = 4 + 2 * LEAD;             // x-pass register window (whole chunks)
+  constexpr int WIN = XS + 2 * LEAD;            // x-pass register window (whole chunks)
   // dynamic shared memory: two plane tiles (plane t+1 streams in while plane t is filtered), the x-pass output,
   // the ext-mapped row offsets / columns of the tile and the plane map of this CTA's z range
   extern __shared__ __align__(16) unsigned char rl_smem[];
@@ -175,26 +181,27 @@ __global__ void __launch_bounds__(32 * (RL_TY / RL_CPT), RL_CPT == 4 ? 2 : 1) rl
     // ---- x pass: strips of 4 outputs; the window is read as whole 16-byte chunks (conflict free: the 8
     // lanes of a quarter warp read 128 contiguous bytes of one tile row)
     const float* tile = sA[buf];
-    for (int item = tid; item < AY * (RL_TX / 4); item += RL_NT) {
-      const int r = item >> 3, s = item & 7;
-      const float4* a = reinterpret_cast<const float4*>(tile + r * PA + s * 4);
+    for (int item = tid; item < AY * (RL_TX / XS); item += RL_NT) {
+      const int r = item / (RL_TX / XS), s = item % (RL_TX / XS);
+      const float4* a = reinterpret_cast<const float4*>(tile + r * PA + s * XS);
       float win[WIN];
 #pragma unroll
       for (int j = 0; j < WIN / 4; ++j) {
         const float4 v = a[j];
         win[4 * j + 0] = v.x; win[4 * j + 1] = v.y; win[4 * j + 2] = v.z; win[4 * j + 3] = v.w;
       }
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      float o[XS];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {  // out[x] = sum_j k[j] * in[x + R - j]; tile column of x0+4s+i is LEAD+4s+i
+      for (int i = 0; i < XS; ++i) o[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {  // out[x] = sum_j k[j] * in[x + R - j]; tile column of x0+XS*s+i is LEAD+XS*s+i
         const float kj = A.kx[j];
-        o0 = fmaf(kj, win[LEAD + 0 + R - j], o0);
-        o1 = fmaf(kj, win[LEAD + 1 + R - j], o1);
-        o2 = fmaf(kj, win[LEAD + 2 + R - j], o2);
-        o3 = fmaf(kj, win[LEAD + 3 + R - j], o3);
+#pragma unroll
+        for (int i = 0; i < XS; ++i) o[i] = fmaf(kj, win[LEAD + i + R - j], o[i]);
       }
-      float* b = sB + r * PB + s * 4;
-      b[0] = o0; b[1] = o1; b[2] = o2; b[3] = o3;
+      float* b = sB + r * PB + s * XS;
+#pragma unroll
+      for (int i = 0; i < XS; ++i) b[i] = o[i];
     }
     __syncthreads();
     // ---- y pass: thread (lane = x, warp = strip of 4 y), then the z shift register
@@ -375,7 +382,8 @@ static int launch_rl_k(const RLArgs& A, cudaStream_t st) {
   constexpr int R = (K - 1) / 2, LEAD = (R + 3) & ~3;
   constexpr int AY = RL_TY + 2 * R, AX = RL_TX + 2 * LEAD;
   dim3 grid((A.nx + RL_TX - 1) / RL_TX, (A.ny + RL_TY - 1) / RL_TY, (A.nz + A.zchunk - 1) / A.zchunk);
-  const size_t smem = (size_t)(2 * AY * AX + AY * (RL_TX + 1)) * sizeof(float) + (size_t)(AY + AX + A.zchunk + K - 1) * sizeof(int);
+  constexpr int PA = (MVF_RL_XS == 8 && (AX % 8) == 0) ? AX + 4 : AX;
+  const size_t smem = (size_t)(2 * AY * PA + AY * (RL_TX + 1)) * sizeof(float) + (size_t)(AY + AX + A.zchunk + K - 1) * sizeof(int);
   auto kern = rl_blur_kernel<K, MODE, CPT>;
   MVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, 32 * (RL_TY / CPT), smem, st>>>(A);

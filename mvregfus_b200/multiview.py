@@ -337,6 +337,10 @@ def fuse_block(tviews_block, weights, params, stack_properties, orig_stack_prope
         weights_kwargs['orig_stack_propertiess'] = orig_stack_propertiess
     if 'orig_stack_propertiess' in fusion_func.__code__.co_varnames:
         fusion_kwargs['orig_stack_propertiess'] = orig_stack_propertiess
+    if weights is None and weights_func == get_weights_simple and fusion_func in (fuse_views_weights, fuse_LR_with_weights_np):
+        # device-resident fast path: same control flow, but the block's weights never travel over PCIe
+        return _fuse_block_device(tviews_block, tviews, params, orig_stack_propertiess, block_stack_properties,
+                                  fusion_func, fusion_kwargs)
     if weights is None and weights_func == get_weights_simple:
         weights = weights_func(**weights_kwargs)
     else:
@@ -349,6 +353,33 @@ def fuse_block(tviews_block, weights, params, stack_properties, orig_stack_prope
     elif len(inds) == 1:
         return tviews_block[inds[0]]
     return fusion_func(tviews, weights=weights, **fusion_kwargs)
+
+
+def _fuse_block_device(tviews_block, tviews, params, orig_stack_propertiess, block_stack_properties, fusion_func,
+                       fusion_kwargs):
+    """Second half of fuse_block (mv:3876-3911) with the blending weights computed and consumed on the device:
+    weights -> drop views whose weights vanish on the block -> trivial cases return the raw view block ->
+    fuse_views_weights / fuse_LR_with_weights_np arithmetic on device tensors -> one D2H of the fused block."""
+    from . import rl
+    dims = [int(s) for s in block_stack_properties['size']]
+    vs = fusion.build_viewset(None, orig_stack_propertiess, params, block_stack_properties, weights="blending")
+    w = fusion.blend_weights(vs, dims, (0, 0, 0), normalise=True)
+    wmax = w.reshape(w.shape[0], -1).amax(dim=1).cpu().numpy()
+    inds = np.where(wmax > 0)[0]
+    if len(inds) == 0:
+        return tviews_block[0]
+    elif len(inds) == 1:
+        return tviews_block[inds[0]]
+    dviews = [fusion.to_device(t) for t in tviews_block]
+    dweights = [w[i] for i in range(w.shape[0])]
+    sp = block_stack_properties
+    if fusion_func == fuse_views_weights:
+        out = fusion.fuse_weighted(dviews, dweights).cpu().numpy()
+        return ImageArray(out, spacing=sp['spacing'], origin=sp['origin'])
+    kw = dict(fusion_kwargs)
+    psfs = [get_psf(params[ip], sp, kw.get('sz', 4), kw.get('sxy', 0.5)) for ip in range(len(params))]
+    est = rl.RLPlan(dviews, dweights, psfs).run(num_iterations=kw.get('num_iterations', 25), tol=kw.get('tol', 5e-5))
+    return ImageArray(est.cpu().numpy().astype(np.uint16), spacing=sp['spacing'], origin=sp['origin'])
 
 
 def _overlap_block(sources, loc, depth, chunk):
