@@ -113,6 +113,22 @@ int mvf_fuse_weighted(int nviews, const void* const* host_view_ptrs, int dtype,
 int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* out, float* out_f32,
                    const int32_t out_dims[3], const int32_t out_origin[3], void* stream);
 
+/* ---- block semantics of fuse_block on the GPU (mv:3817-3916) ----------------------------------------------
+ * fuse_blockwise fuses 128^3 chunks independently and fuse_block drops, per chunk, the views whose transformed
+ * voxels are all zero, short-circuits chunks with 0/1 live views to a raw copy, and drops views whose blending
+ * weights vanish on the chunk.  mvf_chunk_probe computes the two per-(chunk, view) facts on the device
+ * (probe 0: some transformed voxel != 0; probe 1: some raw blending weight > 0; bit v of chunk_flags[chunk],
+ * chunks indexed z-major over `nchunks`, flags must be zeroed by the caller); the caller combines them with the
+ * per-chunk probe-point early-out (host) into chunk_info words: bits 0-7 = views taking part, bit 8 = copy
+ * mode, bits 12-15 = view whose transformed voxels are copied.  mvf_fuse_blend_chunked is mvf_fuse_blend with
+ * those per-chunk decisions applied.  Box origins must be multiples of the 8x8x32 tile. */
+int mvf_chunk_probe(int nviews, const mvf_view* host_views, int probe, const int32_t dims[3],
+                    const int32_t origin[3], uint32_t* chunk_flags, int chunk, const int32_t nchunks[3],
+                    void* stream);
+int mvf_fuse_blend_chunked(int nviews, const mvf_view* host_views, uint16_t* out, const int32_t out_dims[3],
+                           const int32_t out_origin[3], const uint32_t* chunk_info, int chunk,
+                           const int32_t nchunks[3], void* stream);
+
 /* ---- K4/K5: multi-view Richardson-Lucy with weights (fuse_LR_with_weights_np, mv:5545-5749) ------
  * A PSF (get_psf, mv:5376-5418) that is an outer product kz (x) ky (x) kx is passed by its factors
  * (true-convolution taps, odd sizes).  blur(x)[i] = sum_j psf[j] * ext(i + R - j) with the

@@ -19,6 +19,7 @@ MVF_W_OFF, MVF_W_BLEND, MVF_W_BLEND_DCT = 0, 1, 2
 EXPORTS = (
     "mvf_abi_version", "mvf_last_error", "mvf_launch_count",
     "mvf_affine_resample", "mvf_blend_weights", "mvf_fuse_weighted", "mvf_fuse_blend",
+    "mvf_chunk_probe", "mvf_fuse_blend_chunked",
     "mvf_rl_padded_size", "mvf_rl_init_estimate", "mvf_rl_blur", "mvf_rl_ratio", "mvf_rl_correct",
     "mvf_dct_scratch_bytes", "mvf_dct_entropy",
     "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
@@ -74,6 +75,9 @@ def _declare(lib):
     lib.mvf_fuse_weighted.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]
     lib.mvf_fuse_blend.argtypes = [C.c_int, C.POINTER(MvfView), C.c_void_p, C.c_void_p, i32p, i32p, C.c_void_p]
+    lib.mvf_chunk_probe.argtypes = [C.c_int, C.POINTER(MvfView), C.c_int, i32p, i32p, C.c_void_p, C.c_int, i32p, C.c_void_p]
+    lib.mvf_fuse_blend_chunked.argtypes = [C.c_int, C.POINTER(MvfView), C.c_void_p, i32p, i32p, C.c_void_p, C.c_int, i32p,
+                                           C.c_void_p]
     psfp = C.POINTER(MvfRlPsf)
     lib.mvf_rl_padded_size.argtypes = [C.c_int]
     lib.mvf_rl_init_estimate.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_void_p,

@@ -45,9 +45,20 @@ struct KArgs {
   float* outf;    // optional float32 pre-truncation sum
   int dims[3];
   int org[3];
+  // block semantics of fuse_block (mv:3817-3916) on the reference's 128^3 chunk grid of the fused frame
+  const uint32_t* chunk_info;  // K2: per chunk, bits 0-7 = views taking part, bit 8 = copy mode, bits 12-15 = view to copy
+  uint32_t* chunk_flags;       // probe kernels: per chunk, bit v is OR-ed in when view v has data / weight there
+  int flag_bit;                // probe kernels: bit to set (resample probe) 
+  int chunk;                   // chunk edge (128)
+  int nchunk[3];               // chunk grid of the whole fused frame
 };
 
 enum { WT_ZERO = 0, WT_ONE = 1, WT_RAMP = 2, WT_EDGE = 3 };
+
+// index of the 128^3 chunk a tile (fused-frame index of its origin) lies in
+__device__ __forceinline__ int chunk_of(const KArgs& A, int gz0, int gy0, int gx0) {
+  return ((gz0 / A.chunk) * A.nchunk[1] + gy0 / A.chunk) * A.nchunk[2] + gx0 / A.chunk;
+}
 
 // Per-tile, per-view geometry, computed once per CTA (thread v handles view v) and kept in shared memory.
 struct TileView {
@@ -610,8 +621,15 @@ __global__ void __launch_bounds__(NT, MVF_MINB) fuse_blend_kernel(const __grid_c
   int z0, y0, x0;
   if (!tile_origin(A.dims, z0, y0, x0)) return;
   const int tid = threadIdx.x;
+  const uint32_t cinfo = A.chunk_info ? A.chunk_info[chunk_of(A, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2])] : 0xFFu;
+  const bool copy_mode = (cinfo >> 8) & 1u;
+  const int copy_view = (int)((cinfo >> 12) & 15u);
   if (tid < A.nviews) {
     make_tile_view<sizeof(T)>(A.v[tid], z0 + A.org[0], y0 + A.org[1], x0 + A.org[2], true, tv[tid]);
+    if (!copy_mode && !((cinfo >> tid) & 1u)) tv[tid].wclass = WT_ZERO;  // view dropped by fuse_block on this chunk
+    if (copy_mode) {  // 0 or 1 live views: the block is the raw transformed view (mv:3828-3836, 3901-3909)
+      tv[tid].wclass = tid == copy_view ? WT_ONE : WT_ZERO;
+    }
     if (tv[tid].wclass == WT_ZERO) tv[tid].skip = 1;  // zero weight on the whole tile: the view contributes nothing
   }
   __syncthreads();
@@ -710,7 +728,22 @@ __global__ void __launch_bounds__(NT) resample_kernel(const __grid_constant__ KA
       }
     }
   }
-  if (y >= A.dims[1] || x >= A.dims[2]) return;
+  const bool in_box = y < A.dims[1] && x < A.dims[2];
+  if (A.chunk_flags) {  // probe mode: does the transformed view have a non-zero voxel in this chunk? (mv:3828-3830)
+    bool any = false;
+    if (in_box) {
+#pragma unroll
+      for (int k = 0; k < TZ; ++k) {
+        if (z0 + k >= A.dims[0]) break;
+        any = any || (sizeof(T) == 2 ? (A.rule == MVF_RULE_SCIPY ? round_half_up_u16(val[k]) : clamp_trunc_u16(val[k])) > 0u
+                                     : val[k] > 0.f);
+      }
+    }
+    if (__syncthreads_or(any) && tid == 0)
+      atomicOr(A.chunk_flags + chunk_of(A, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2]), 1u << A.flag_bit);
+    return;
+  }
+  if (!in_box) return;
   T* dst = reinterpret_cast<T*>(A.out);
 #pragma unroll
   for (int k = 0; k < TZ; ++k) {
@@ -739,7 +772,23 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const __grid_constant
   const int gz = z0 + A.org[0], gy = y + A.org[1], gx = x + A.org[2];
   float wsum[TZ];
   column_weights(A, tv, wsm, gz, gy, gx, wsum);
-  if (y >= A.dims[1] || x >= A.dims[2]) return;
+  const bool in_box = y < A.dims[1] && x < A.dims[2];
+  if (A.chunk_flags) {  // probe mode: which views have a non-zero blending weight somewhere in this chunk? (mv:3902-3904)
+    for (int v = 0; v < A.nviews; ++v) {
+      bool any = false;
+      if (in_box) {
+#pragma unroll
+        for (int k = 0; k < TZ; ++k) {
+          if (z0 + k >= A.dims[0]) break;
+          any = any || wsm[(v * TZ + k) * NT + tid] > 0.f;
+        }
+      }
+      if (__syncthreads_or(any) && tid == 0)
+        atomicOr(A.chunk_flags + chunk_of(A, z0 + A.org[0], y0 + A.org[1], x0 + A.org[2]), 1u << v);
+    }
+    return;
+  }
+  if (!in_box) return;
   float* out = reinterpret_cast<float*>(A.out);
   const size_t vol = (size_t)A.dims[0] * A.dims[1] * A.dims[2];
   for (int v = 0; v < A.nviews; ++v) {
@@ -895,6 +944,68 @@ extern "C" int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* 
   if (host_views[0].dtype == MVF_U16)
     return out_f32 ? launch_tiles(fuse_blend_kernel<uint16_t, true>, A, smem, st) : launch_tiles(fuse_blend_kernel<uint16_t, false>, A, smem, st);
   return out_f32 ? launch_tiles(fuse_blend_kernel<float, true>, A, smem, st) : launch_tiles(fuse_blend_kernel<float, false>, A, smem, st);
+}
+
+static int set_chunks(KArgs& A, const uint32_t* info, uint32_t* flags, int chunk, const int32_t nchunk[3], const int32_t org[3]) {
+  if (!info && !flags) return MVF_OK;
+  if (chunk <= 0 || chunk % TX != 0 || !nchunk) return fail(MVF_ERR_INVALID, "%s%s", "chunk edge must be a positive multiple of 32");
+  if (org[0] % TZ || org[1] % TY || org[2] % TX)
+    return fail(MVF_ERR_INVALID, "%s%s", "with chunk tables the box origin must be a multiple of the 8x8x32 tile");
+  A.chunk_info = info; A.chunk_flags = flags; A.chunk = chunk;
+  for (int d = 0; d < 3; ++d) A.nchunk[d] = nchunk[d];
+  return MVF_OK;
+}
+
+extern "C" int mvf_fuse_blend_chunked(int nviews, const mvf_view* host_views, uint16_t* out, const int32_t out_dims[3],
+                                      const int32_t out_origin[3], const uint32_t* chunk_info, int chunk,
+                                      const int32_t nchunks[3], void* stream) {
+  MVF_CHECK_ARG(nviews >= 1 && nviews <= MVF_MAX_VIEWS, "nviews must be in [1, MVF_MAX_VIEWS]");
+  MVF_CHECK_ARG(host_views && out && out_dims && out_origin && chunk_info && nchunks, "NULL argument");
+  MVF_CHECK_ARG(out_dims[0] > 0 && out_dims[1] > 0 && out_dims[2] > 0, "out_dims must be positive");
+  KArgs A;
+  size_t brick;
+  int rc = fill_args(A, nviews, host_views, true, out, nullptr, out_dims, out_origin, &brick);
+  if (rc) return rc;
+  rc = set_chunks(A, chunk_info, nullptr, chunk, nchunks, out_origin);
+  if (rc) return rc;
+  const size_t smem = brick + (size_t)nviews * TILE_VOX * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  return host_views[0].dtype == MVF_U16 ? launch_tiles(fuse_blend_kernel<uint16_t, false>, A, smem, st)
+                                        : launch_tiles(fuse_blend_kernel<float, false>, A, smem, st);
+}
+
+// chunk_flags[chunk] |= 1 << v for every view v whose transformed (scipy-rule) voxels are not all zero on the chunk
+// (probe == 0) or whose raw blending weight is positive somewhere on the chunk (probe == 1).
+extern "C" int mvf_chunk_probe(int nviews, const mvf_view* host_views, int probe, const int32_t dims[3],
+                               const int32_t origin[3], uint32_t* chunk_flags, int chunk, const int32_t nchunks[3],
+                               void* stream) {
+  MVF_CHECK_ARG(nviews >= 1 && nviews <= MVF_MAX_VIEWS, "nviews must be in [1, MVF_MAX_VIEWS]");
+  MVF_CHECK_ARG(host_views && dims && origin && chunk_flags && nchunks, "NULL argument");
+  MVF_CHECK_ARG(probe == 0 || probe == 1, "probe must be 0 (data) or 1 (weights)");
+  cudaStream_t st = as_stream(stream);
+  if (probe == 1) {
+    KArgs A;
+    size_t brick;
+    int rc = fill_args(A, nviews, host_views, false, nullptr, nullptr, dims, origin, &brick);
+    if (rc) return rc;
+    rc = set_chunks(A, nullptr, chunk_flags, chunk, nchunks, origin);
+    if (rc) return rc;
+    return launch_tiles(blend_weights_kernel, A, (size_t)nviews * TILE_VOX * sizeof(float), st);
+  }
+  for (int v = 0; v < nviews; ++v) {
+    KArgs A;
+    size_t brick;
+    int rc = fill_args(A, 1, host_views + v, true, nullptr, nullptr, dims, origin, &brick);
+    if (rc) return rc;
+    rc = set_chunks(A, nullptr, chunk_flags, chunk, nchunks, origin);
+    if (rc) return rc;
+    A.rule = MVF_RULE_SCIPY;
+    A.flag_bit = v;
+    rc = host_views[v].dtype == MVF_U16 ? launch_tiles(resample_kernel<uint16_t>, A, brick, st)
+                                        : launch_tiles(resample_kernel<float>, A, brick, st);
+    if (rc) return rc;
+  }
+  return MVF_OK;
 }
 
 extern "C" int mvf_blend_weights(int nviews, const mvf_view* host_views, float* weights_out, const int32_t dims[3],

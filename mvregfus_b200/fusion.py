@@ -120,7 +120,7 @@ class ViewSet:
 
 
 def build_viewset(tensors, orig_stack_propertiess, params, stack_properties, weights="blending",
-                  coarse=None, view_dims=None):
+                  coarse=None, view_dims=None, probe=True):
     """Fill ``mvf_view`` for every view.  ``tensors`` may be None (weights only).  ``coarse`` is an optional
     ``(grids (V,cz,cy,cx) float32, origin[3], spacing[3])`` for the DCT mode.  ``weights`` in
     {'blending', 'dct', None}."""
@@ -152,7 +152,7 @@ def build_viewset(tensors, orig_stack_propertiess, params, stack_properties, wei
         s.weight_mode = _cabi.MVF_W_OFF
         if weights is None:
             continue
-        if not probe_any_inside(osp, params[i], stack_properties, 5):
+        if probe and not probe_any_inside(osp, params[i], stack_properties, 5):
             continue  # zero weights for this view in this box (mv:3518-3522)
         prof, sigspacing = border_profiles(osp)
         Mw, offw = index_space_affine(params[i], sigspacing, v_or + 1 * v_sp, out_sp, out_or)
