@@ -401,7 +401,7 @@ def run_b200(args):
             line["rl"] = run_rl(dev, rank, world)
         if not args.no_cpu_baseline:
             views_host = [p.numpy() for p in pinned]
-            gv, dt, sample = cpu_baseline(views_host, params, props, sp, box=96, threads=1)
+            gv, dt, sample = cpu_baseline(views_host, params, props, sp, box=192, threads=1)
             line["cpu_baseline"] = {"value": gv, "unit": "Gvoxel/s", "cores": 1, "kind": "port", "sample": sample,
                                     "seconds": dt}
         print(json.dumps(line))
