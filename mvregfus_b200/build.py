@@ -17,7 +17,7 @@ LIBNAME = "libmvregfus_b200.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas=-v",
-]
+] + os.environ.get("MVF_NVCC_EXTRA", "").split()   # e.g. -DMVF_RL_TUNE (extra tile configurations for tuning)
 
 
 def _nvcc():

@@ -16,10 +16,14 @@ def _axis_case(shape=(48, 40, 56), nviews=2, seed=5):
     return tv, w, params, sp
 
 
+@pytest.mark.parametrize("kernel", ["v1", "v2"])   # v2: FFMA2 plane-pair kernel (opt-in, PSFs up to 19 taps)
 @pytest.mark.parametrize("ksize", [(7, 7, 7), (19, 19, 19), (5, 9, 13), (25, 25, 25), (37, 37, 37), (9, 31, 43)])
-def test_blur_matches_closed_form(cuda, ksize):
+def test_blur_matches_closed_form(cuda, ksize, kernel, monkeypatch):
     import torch
     from mvregfus_b200 import rl
+    if kernel == "v2" and max(ksize) > 19:
+        pytest.skip("pair kernel covers PSFs up to 19 taps")
+    monkeypatch.setenv("MVF_RL_KERNEL", kernel)
     rng = np.random.default_rng(1)
     x = rng.random((48, 50, 70)).astype(np.float32) * 100
     f = [np.exp(-0.5 * ((np.arange(k) - k // 2) / (0.15 * k + 0.5)) ** 2).astype(np.float32) for k in ksize]
@@ -96,12 +100,14 @@ def test_rl_oblique_views_dense_psf(cuda, dense_mode, monkeypatch):
     assert float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0))) <= 1e-3
 
 
+@pytest.mark.parametrize("kernel", ["v1", "v2"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_rl_slab_sharded_equals_whole(cuda, world):
+def test_rl_slab_sharded_equals_whole(cuda, world, kernel, monkeypatch):
     """z-slab sharded RL (ranks emulated on one GPU, same kernels, same halo plane movement as the NCCL ring)
     reproduces the single-GPU whole-volume result bit for bit, including the wrap-around low edge."""
     import torch
     from mvregfus_b200 import fusion, rl, slab, multiview as mv
+    monkeypatch.setenv("MVF_RL_KERNEL", kernel)
     tv, w, params, sp = _axis_case(shape=(72, 40, 48), nviews=2)
     psfs = [mv.get_psf(p, sp, 2, 1) for p in params]   # 7^3
     dv, dw = [fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w]
