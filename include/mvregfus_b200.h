@@ -203,6 +203,22 @@ int mvf_dct_entropy(const void* tview, int dtype, const int32_t dims[3], int bin
                     const int32_t nblocks[3], const int32_t* jobs, int njobs, const double* cosm,
                     double* scratch, double* q_out, void* stream);
 
+/* ---- steps either side of the path: .ims pyramid and raw-view preprocessing ----------------
+ * mvf_subsample: out = in[::step[0], ::step[1], ::step[2]] (subsample_data, imaris.py:764-765); out extents are
+ * ceil(in_dims / step).  The writer applies it cumulatively level after level (imaris.py:146-148, 321-323).
+ * mvf_range_u16 / mvf_hist_u16: the two device passes of np.histogram(data, 256) on uint16 data (imaris.py:155,
+ * 324): minmax[0..1] = min, max; `lut` maps every uint16 value to its bin (built on the host with numpy's own
+ * binning once the range is known), counts[256] receives the histogram.
+ * mvf_background_u16: out = (in - level) * (in > level) in uint16 arithmetic (multiview.py:316).
+ * mvf_bin_shrink: sitk.BinShrink (mv_utils.py:288-311): mean over factors[0] x factors[1] x factors[2] (z,y,x)
+ * bins, partial bins dropped (out extents floor(in_dims / factors)), uint16 results rounded half up. */
+int mvf_subsample(const void* in, int dtype, const int32_t in_dims[3], const int32_t step[3], void* out, void* stream);
+int mvf_range_u16(const uint16_t* in, size_t n, uint32_t* minmax, void* stream);
+int mvf_hist_u16(const uint16_t* in, size_t n, const uint8_t* lut, uint64_t* counts, void* stream);
+int mvf_background_u16(const uint16_t* in, uint16_t* out, size_t n, uint32_t level, void* stream);
+int mvf_bin_shrink(const void* in, int dtype, const int32_t in_dims[3], const int32_t factors[3], void* out,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ EXPORTS = (
     "mvf_dct_scratch_bytes", "mvf_dct_entropy",
     "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
     "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur",
+    "mvf_subsample", "mvf_range_u16", "mvf_hist_u16", "mvf_background_u16", "mvf_bin_shrink",
 )
 MVF_RL_KMAX = 43
 
@@ -97,6 +98,11 @@ def _declare(lib):
     lib.mvf_dct_scratch_bytes.argtypes = [C.c_int, C.POINTER(C.c_int)]
     lib.mvf_dct_entropy.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int, C.c_int, i32p, C.c_void_p, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mvf_subsample.argtypes = [C.c_void_p, C.c_int, i32p, i32p, C.c_void_p, C.c_void_p]
+    lib.mvf_range_u16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.mvf_hist_u16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mvf_background_u16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.mvf_bin_shrink.argtypes = [C.c_void_p, C.c_int, i32p, i32p, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version", "mvf_rl_padded_size", "mvf_dct_scratch_bytes"):

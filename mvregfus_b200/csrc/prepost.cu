@@ -1,0 +1,263 @@
+// Steps either side of the fusion path, sm_100a.  All of them are pure streaming
+// work bound by HBM bandwidth: one pass, 16-byte accesses where the layout allows, grids sized in multiples of
+// the SM count.
+//   * output pyramid of the .ims writer: strided subsampling data[::sz, ::sy, ::sx]   (imaris.py:764-765,
+//     applied cumulatively level after level, imaris.py:146-148 / 321-323) and the 256-bin histogram of each
+//     level (np.histogram(data, 256), imaris.py:155, 324);
+//   * raw-view preprocessing: background subtraction (stack - bg) * (stack > bg)       (multiview.py:316) and
+//     integer binning sitk.BinShrink                                                    (mv_utils.py:288-311).
+#include "common.cuh"
+
+namespace mvf {
+
+// ---- strided subsampling ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) subsample_kernel(const T* __restrict__ in, T* __restrict__ out, int nz, int ny, int nx,
+                                                        int oz, int oy, int ox, int sz, int sy, int sx) {
+  const size_t total = (size_t)oz * oy * ox;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int x = (int)(i % ox);
+    const size_t r = i / ox;
+    const int y = (int)(r % oy), z = (int)(r / oy);
+    out[i] = in[((size_t)z * sz * ny + (size_t)y * sy) * nx + (size_t)x * sx];
+  }
+}
+
+// uint16, x step 2, 16-byte aligned rows: a thread turns 8 consecutive source voxels (one LDG.128) into 4 outputs
+// (one STG.64), so the even rows of the even planes are streamed with full sectors.
+__global__ void __launch_bounds__(256) subsample_x2_u16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int ny, int nx,
+                                                               int oz, int oy, int ox, int sz, int sy) {
+  const int cpr = nx / 8;                       // chunks per source row (ox == nx / 2 == 4 * cpr)
+  const size_t total = (size_t)oz * oy * cpr;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int c = (int)(i % cpr);
+    const size_t r = i / cpr;
+    const int y = (int)(r % oy), z = (int)(r / oy);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ((size_t)z * sz * ny + (size_t)y * sy) * nx) + c);
+    const uint2 o = make_uint2((q.x & 0xFFFFu) | (q.y << 16), (q.z & 0xFFFFu) | (q.w << 16));
+    reinterpret_cast<uint2*>(out + ((size_t)z * oy + y) * ox)[c] = o;
+  }
+}
+
+// ---- value range + 256-bin histogram of uint16 data --------------------------------------------------------
+// np.histogram(data, 256) bins over [min, max] with float64 edges.  For uint16 data the bin of a voxel is a
+// function of its value alone, so the host derives a 65536-entry value -> bin table FROM NUMPY ITSELF (exact by
+// construction) once the range is known; the device only counts.  Pass 1: min/max.  Pass 2: table look-up
+// (64 KB of shared memory) + per-warp private 256-bin counters, merged with one atomic per bin and CTA.
+__global__ void __launch_bounds__(256) range_u16_kernel(const uint16_t* __restrict__ in, size_t n, unsigned* __restrict__ minmax) {
+  unsigned lo = 0xFFFFu, hi = 0u;
+  const size_t nvec = n / 8;
+  const uint4* __restrict__ v = reinterpret_cast<const uint4*>(in);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+    const uint4 q = __ldg(v + i);
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned a = w[j] & 0xFFFFu, b = w[j] >> 16;
+      lo = min(lo, min(a, b));
+      hi = max(hi, max(a, b));
+    }
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = nvec * 8 + threadIdx.x; i < n; i += 256) { lo = min(lo, (unsigned)in[i]); hi = max(hi, (unsigned)in[i]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
+}
+
+__global__ void __launch_bounds__(256) hist_u16_kernel(const uint16_t* __restrict__ in, size_t n, const uint8_t* __restrict__ lut,
+                                                       unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char hs[];
+  uint8_t* slut = hs;                                            // 65536 bytes
+  unsigned* sc = reinterpret_cast<unsigned*>(hs + 65536);        // 8 warps x 256 counters
+  for (int i = threadIdx.x; i < 65536 / 16; i += 256) reinterpret_cast<uint4*>(slut)[i] = __ldg(reinterpret_cast<const uint4*>(lut) + i);
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) sc[i] = 0u;
+  __syncthreads();
+  unsigned* mine = sc + (threadIdx.x >> 5) * 256;
+  const size_t nvec = n / 8;
+  const uint4* __restrict__ v = reinterpret_cast<const uint4*>(in);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+    const uint4 q = __ldg(v + i);
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    // neighbouring voxels often share a bin: merge equal consecutive bins before touching shared memory
+    unsigned cur = slut[w[0] & 0xFFFFu], run = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const unsigned b = slut[h ? (w[j] >> 16) : (w[j] & 0xFFFFu)];
+        if (b == cur) { ++run; } else { atomicAdd(mine + cur, run); cur = b; run = 1; }
+      }
+    }
+    atomicAdd(mine + cur, run);
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = nvec * 8 + threadIdx.x; i < n; i += 256) atomicAdd(mine + slut[in[i]], 1u);
+  __syncthreads();
+  unsigned s = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += sc[w * 256 + threadIdx.x];
+  if (s) atomicAdd(counts + threadIdx.x, (unsigned long long)s);
+}
+
+// ---- background subtraction (uint16): (stack - bg) * (stack > bg) with numpy's uint16 wrap semantics ------------
+__global__ void __launch_bounds__(256) background_u16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, size_t n,
+                                                             unsigned bg) {
+  const size_t nvec = n / 8;
+  const uint4* __restrict__ v = reinterpret_cast<const uint4*>(in);
+  uint4* __restrict__ o = reinterpret_cast<uint4*>(out);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+    const uint4 q = __ldg(v + i);
+    unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned a = w[j] & 0xFFFFu, b = w[j] >> 16;
+      const unsigned ra = a > bg ? a - bg : 0u, rb = b > bg ? b - bg : 0u;
+      w[j] = ra | (rb << 16);
+    }
+    o[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = nvec * 8 + threadIdx.x; i < n; i += 256) { const unsigned a = in[i]; out[i] = (uint16_t)(a > bg ? a - bg : 0u); }
+}
+
+// ---- BinShrink: mean over fz x fy x fx bins, partial bins dropped; integer output rounded half up -------------
+// (itk::BinShrinkImageFilter: accumulate in the real type, divide by the bin volume, RoundIfInteger)
+template <typename T>
+__global__ void __launch_bounds__(256) bin_shrink_kernel(const T* __restrict__ in, T* __restrict__ out, int ny, int nx, int oz, int oy,
+                                                         int ox, int fz, int fy, int fx) {
+  const size_t total = (size_t)oz * oy * ox;
+  const double num = (double)fz * fy * fx;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int x = (int)(i % ox);
+    const size_t r = i / ox;
+    const int y = (int)(r % oy), z = (int)(r / oy);
+    double s = 0.0;
+    for (int a = 0; a < fz; ++a)
+      for (int b = 0; b < fy; ++b) {
+        const T* __restrict__ row = in + ((size_t)(z * fz + a) * ny + (size_t)(y * fy + b)) * nx + (size_t)x * fx;
+        for (int c = 0; c < fx; ++c) s += (double)row[c];
+      }
+    const double m = s / num;
+    if (sizeof(T) == 2) out[i] = (T)(unsigned)floor(m + 0.5);
+    else out[i] = (T)m;
+  }
+}
+
+// uint16, x factor 2, 16-byte aligned rows: exact integer accumulation (a bin holds < 2^16 voxels) and
+// floor(sum / num + 0.5) == (2 sum + num) / (2 num) in integers (the quotient never comes within 1/(2 num) of a tie
+// without being one), 8 source voxels per LDG.128, 4 outputs per STG.64.
+// exact x / d for x < 2^31, d < 2^16 (quotient < 2^16): float estimate, one correction step either way
+__device__ __forceinline__ unsigned div_small(unsigned x, unsigned d, float inv) {
+  unsigned q = (unsigned)((float)x * inv);
+  if (q * d > x) --q;
+  if ((q + 1) * d <= x) ++q;
+  return q;
+}
+
+__global__ void __launch_bounds__(256) bin_shrink_x2_u16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int ny, int nx,
+                                                                int oz, int oy, int ox, int fz, int fy) {
+  const int cpr = ox / 4;                        // output chunks (4 voxels) per row; the source row has >= 8 * cpr voxels
+  const size_t total = (size_t)oz * oy * cpr;
+  const unsigned num = (unsigned)(fz * fy * 2);
+  const float inv = 1.0f / (float)(2 * num);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int c = (int)(i % cpr);
+    const size_t r = i / cpr;
+    const int y = (int)(r % oy), z = (int)(r / oy);
+    unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int a = 0; a < fz; ++a)
+#pragma unroll 4
+      for (int b = 0; b < fy; ++b) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ((size_t)(z * fz + a) * ny + (size_t)(y * fy + b)) * nx) + c);
+        s0 += (q.x & 0xFFFFu) + (q.x >> 16); s1 += (q.y & 0xFFFFu) + (q.y >> 16);
+        s2 += (q.z & 0xFFFFu) + (q.z >> 16); s3 += (q.w & 0xFFFFu) + (q.w >> 16);
+      }
+    const unsigned r0 = div_small(2 * s0 + num, 2 * num, inv), r1 = div_small(2 * s1 + num, 2 * num, inv);
+    const unsigned r2 = div_small(2 * s2 + num, 2 * num, inv), r3 = div_small(2 * s3 + num, 2 * num, inv);
+    reinterpret_cast<uint2*>(out + ((size_t)z * oy + y) * ox)[c] = make_uint2(r0 | (r1 << 16), r2 | (r3 << 16));
+  }
+}
+
+static int stream_grid(size_t items) {
+  const size_t want = (items + 255) / 256, cap = (size_t)sm_count() * 8;   // 8 CTAs of 256 threads per SM
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace mvf
+
+using namespace mvf;
+
+extern "C" int mvf_subsample(const void* in, int dtype, const int32_t in_dims[3], const int32_t step[3], void* out, void* stream) {
+  MVF_CHECK_ARG(in && out && in_dims && step, "NULL argument");
+  MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
+  for (int d = 0; d < 3; ++d) MVF_CHECK_ARG(in_dims[d] > 0 && step[d] >= 1, "dims must be positive and steps >= 1");
+  const int oz = (in_dims[0] + step[0] - 1) / step[0], oy = (in_dims[1] + step[1] - 1) / step[1], ox = (in_dims[2] + step[2] - 1) / step[2];
+  const int grid = stream_grid((size_t)oz * oy * ox);
+  cudaStream_t st = as_stream(stream);
+  const bool al = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (dtype == MVF_U16 && step[2] == 2 && in_dims[2] % 16 == 0 && al)
+    subsample_x2_u16_kernel<<<stream_grid((size_t)oz * oy * (in_dims[2] / 8)), 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, in_dims[1], in_dims[2], oz, oy, ox, step[0], step[1]);
+  else if (dtype == MVF_U16)
+    subsample_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, in_dims[0], in_dims[1], in_dims[2], oz, oy, ox, step[0], step[1], step[2]);
+  else
+    subsample_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, in_dims[0], in_dims[1], in_dims[2], oz, oy, ox, step[0], step[1], step[2]);
+  MVF_LAUNCHED();
+  return MVF_OK;
+}
+
+extern "C" int mvf_range_u16(const uint16_t* in, size_t n, uint32_t* minmax, void* stream) {
+  MVF_CHECK_ARG(in && minmax && n > 0, "NULL argument or empty input");
+  MVF_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15u) == 0, "input must be 16-byte aligned");
+  const uint32_t init[2] = {0xFFFFu, 0u};
+  MVF_CUDA(cudaMemcpyAsync(minmax, init, sizeof(init), cudaMemcpyHostToDevice, as_stream(stream)));
+  range_u16_kernel<<<stream_grid(n / 8 + 1), 256, 0, as_stream(stream)>>>(in, n, minmax);
+  MVF_LAUNCHED();
+  return MVF_OK;
+}
+
+extern "C" int mvf_hist_u16(const uint16_t* in, size_t n, const uint8_t* lut, uint64_t* counts, void* stream) {
+  MVF_CHECK_ARG(in && lut && counts && n > 0, "NULL argument or empty input");
+  MVF_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (reinterpret_cast<uintptr_t>(lut) & 15u) == 0, "input and table must be 16-byte aligned");
+  const size_t smem = 65536 + 8 * 256 * sizeof(unsigned);
+  MVF_CUDA(cudaFuncSetAttribute(hist_u16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MVF_CUDA(cudaMemsetAsync(counts, 0, 256 * sizeof(uint64_t), as_stream(stream)));
+  const size_t want = (n / 8 + 255) / 256 + 1, cap = (size_t)sm_count() * 3;   // 72 KB of shared memory: 3 CTAs per SM
+  hist_u16_kernel<<<(int)(want < cap ? want : cap), 256, smem, as_stream(stream)>>>(in, n, lut, reinterpret_cast<unsigned long long*>(counts));
+  MVF_LAUNCHED();
+  return MVF_OK;
+}
+
+extern "C" int mvf_background_u16(const uint16_t* in, uint16_t* out, size_t n, uint32_t level, void* stream) {
+  MVF_CHECK_ARG(in && out, "NULL argument");
+  MVF_CHECK_ARG(level <= 65535u, "background level must fit uint16");
+  MVF_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0, "buffers must be 16-byte aligned");
+  if (n == 0) return MVF_OK;
+  background_u16_kernel<<<stream_grid(n / 8 + 1), 256, 0, as_stream(stream)>>>(in, out, n, level);
+  MVF_LAUNCHED();
+  return MVF_OK;
+}
+
+extern "C" int mvf_bin_shrink(const void* in, int dtype, const int32_t in_dims[3], const int32_t factors[3], void* out, void* stream) {
+  MVF_CHECK_ARG(in && out && in_dims && factors, "NULL argument");
+  MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
+  int o[3];
+  for (int d = 0; d < 3; ++d) {
+    MVF_CHECK_ARG(factors[d] >= 1 && in_dims[d] >= factors[d], "bin factors must be >= 1 and <= the extent");
+    o[d] = in_dims[d] / factors[d];
+  }
+  const int grid = stream_grid((size_t)o[0] * o[1] * o[2]);
+  cudaStream_t st = as_stream(stream);
+  const bool al = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (dtype == MVF_U16 && factors[2] == 2 && in_dims[2] % 16 == 0 && al && factors[0] * factors[1] <= 16384)
+    bin_shrink_x2_u16_kernel<<<stream_grid((size_t)o[0] * o[1] * (o[2] / 4)), 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, in_dims[1], in_dims[2], o[0], o[1], o[2], factors[0], factors[1]);
+  else if (dtype == MVF_U16)
+    bin_shrink_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, in_dims[1], in_dims[2], o[0], o[1], o[2], factors[0], factors[1], factors[2]);
+  else
+    bin_shrink_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, in_dims[1], in_dims[2], o[0], o[1], o[2], factors[0], factors[1], factors[2]);
+  MVF_LAUNCHED();
+  return MVF_OK;
+}

@@ -76,3 +76,9 @@ def index_space_affine(p, in_spacing, in_origin, out_spacing, out_origin):
     matrix = np.dot(Sy_inv, np.dot(A, Sx))
     offset = np.dot(Sy_inv, c - np.asarray(in_origin, dtype=np.float64) + np.dot(A, np.asarray(out_origin, dtype=np.float64)))
     return matrix, offset
+
+
+def bin_stack(im, bin_factors=np.array([1, 1, 1])):
+    """mv_utils.bin_stack (reference: mv_utils.py:288-311) on the device: see mvregfus_b200.prepost.bin_stack."""
+    from .prepost import bin_stack as _bin_stack
+    return _bin_stack(im, bin_factors)

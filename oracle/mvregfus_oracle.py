@@ -710,3 +710,63 @@ def overlap_full(tviews, nchunks, chunk=CHUNK):
     for iv, t in enumerate(tviews):
         full[iv, :s[0], :s[1], :s[2]] = np.asarray(t)
     return full
+
+
+# ---------------------------------------------------------------------------------------------------
+# steps either side of the path
+# ---------------------------------------------------------------------------------------------------
+def subsample_data(data, subsamp):
+    """imaris.py:764-765."""
+    return data[0::int(subsamp[0]), 0::int(subsamp[1]), 0::int(subsamp[2])]
+
+
+def pyramid_levels(array, subsamp=((1, 1, 1), (2, 2, 2), (4, 4, 4), (8, 8, 8))):
+    """Level loop of np_to_ims (imaris.py:316-331): the factors are applied cumulatively, each level gets
+    np.histogram(data, 256)."""
+    data = np.squeeze(np.asarray(array))
+    levels = []
+    for ss in subsamp:
+        if any(i > 1 for i in ss):
+            data = subsample_data(data, ss)
+        hist, edges = np.histogram(data, 256)
+        levels.append({"data": data, "hist": hist, "edges": edges})
+    return levels
+
+
+def subtract_background(stack, background_level):
+    """multiview.py:316: (stack - background_level) * (stack > background_level), numpy dtype rules of a
+    uint16 stack and a Python int level (the difference wraps, the mask zeroes the wrapped entries)."""
+    stack = np.asarray(stack)
+    level = np.asarray(background_level).astype(stack.dtype) if np.issubdtype(stack.dtype, np.integer) else background_level
+    return (stack - level) * (stack > level)
+
+
+def bin_shrink(arr, factors_zyx):
+    """RESTATEMENT of itk::BinShrinkImageFilter (SimpleITK is absent: parity unpinned): mean over the bins in the
+    real type, partial bins dropped, integer outputs rounded half up (itk::Math::Round)."""
+    arr = np.asarray(arr)
+    f = [int(x) for x in factors_zyx]
+    o = [n // k for n, k in zip(arr.shape, f)]
+    a = arr[:o[0] * f[0], :o[1] * f[1], :o[2] * f[2]].astype(np.float64)
+    a = a.reshape(o[0], f[0], o[1], f[1], o[2], f[2])
+    # accumulation order of the filter: z, then y, then x offsets inside the bin
+    s = np.zeros(o, dtype=np.float64)
+    for dz in range(f[0]):
+        for dy in range(f[1]):
+            for dx in range(f[2]):
+                s += a[:, dz, :, dy, :, dx]
+    m = s / float(f[0] * f[1] * f[2])
+    if np.issubdtype(arr.dtype, np.integer):
+        return np.floor(m + 0.5).astype(arr.dtype)
+    return m.astype(arr.dtype)
+
+
+def bin_stack(im, bin_factors=np.array([1, 1, 1])):
+    """mv_utils.py:288-311 with bin_shrink in place of sitk.BinShrink (factors arrive in x,y,z order)."""
+    if np.allclose(bin_factors, [1] * len(bin_factors)):
+        return im
+    bin_factors = np.array(bin_factors)
+    binned_spacing = im.spacing * bin_factors[::-1]
+    binned_origin = im.origin + (binned_spacing - im.spacing) / 2.
+    out = bin_shrink(np.asarray(im), [int(i) for i in bin_factors][::-1])
+    return ImageArray(out, spacing=binned_spacing, origin=binned_origin, rotation=im.rotation)
