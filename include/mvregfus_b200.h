@@ -172,6 +172,23 @@ int mvf_rl_correct(const float* ratio, const int32_t* zmap, const int32_t dims[3
                    const float* weights, float* corr, int first, int last, float* est,
                    int64_t est_offset, double* sum_out, void* stream);
 
+/* Streaming formulation of the same blur for separable PSFs (default when rows are 16-byte aligned): mvf_rl_xy runs
+ * the x and y passes on every plane of the input buffer (`nplanes` planes of dims[1] x dims[2]; for a z-slab that
+ * includes the halo planes), mvf_rl_*_z run the z pass through the plane map on that intermediate and apply the
+ * same epilogues as mvf_rl_blur / mvf_rl_ratio / mvf_rl_correct.  Two kernels without shared memory or barriers
+ * replace one fused kernel; the intermediate costs one extra float32 round trip through HBM.
+ * mvf_rl_stream_supported: 1 if the PSF is separable and dims[2] is a multiple of the vector width (4 columns up
+ * to 19 taps, 2 beyond). */
+int mvf_rl_stream_supported(const int32_t dims[3], const mvf_rl_psf* psf);
+int mvf_rl_xy(const float* in, int32_t nplanes, const int32_t dims[3], const mvf_rl_psf* psf, float* out, void* stream);
+int mvf_rl_blur_z(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf, float* out,
+                  void* stream);
+int mvf_rl_ratio_z(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                   const void* view, int dtype, const float* weights, float* ratio_out, void* stream);
+int mvf_rl_correct_z(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                     const float* weights, float* corr, int first, int last, float* est, int64_t est_offset,
+                     double* sum_out, void* stream);
+
 /* ---- RL, general PSFs: cuFFT circular convolution with the reference's padding (mv:5647-5673) ------------
  * For PSFs that are not outer products (oblique views).  The padded extents are the next 2^a3^b5^c7^d >=
  * n + K - 1 per axis (the reference uses n + K + 1; the extra entries only hold zeros, the reflected tail and

@@ -24,6 +24,7 @@ EXPORTS = (
     "mvf_dct_scratch_bytes", "mvf_dct_entropy",
     "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
     "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur",
+    "mvf_rl_stream_supported", "mvf_rl_xy", "mvf_rl_blur_z", "mvf_rl_ratio_z", "mvf_rl_correct_z",
     "mvf_subsample", "mvf_range_u16", "mvf_hist_u16", "mvf_background_u16", "mvf_bin_shrink",
 )
 MVF_RL_KMAX = 43
@@ -87,6 +88,11 @@ def _declare(lib):
     lib.mvf_rl_ratio.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mvf_rl_correct.argtypes = [C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_stream_supported.argtypes = [i32p, psfp]
+    lib.mvf_rl_xy.argtypes = [C.c_void_p, C.c_int32, i32p, psfp, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_blur_z.argtypes = lib.mvf_rl_blur.argtypes
+    lib.mvf_rl_ratio_z.argtypes = lib.mvf_rl_ratio.argtypes
+    lib.mvf_rl_correct_z.argtypes = lib.mvf_rl_correct.argtypes
     lib.mvf_rl_fft_padded_dims.argtypes = [i32p, i32p, i32p]
     lib.mvf_rl_fft_plan_create.argtypes = [i32p, i32p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
     lib.mvf_rl_fft_plan_set_workspace.argtypes = [C.c_void_p, C.c_void_p]
@@ -105,7 +111,8 @@ def _declare(lib):
     lib.mvf_bin_shrink.argtypes = [C.c_void_p, C.c_int, i32p, i32p, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version", "mvf_rl_padded_size", "mvf_dct_scratch_bytes"):
+        if name not in ("mvf_last_error", "mvf_launch_count", "mvf_abi_version", "mvf_rl_padded_size", "mvf_dct_scratch_bytes",
+                        "mvf_rl_stream_supported"):
             fn.restype = C.c_int
 
 

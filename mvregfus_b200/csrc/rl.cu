@@ -395,6 +395,7 @@ static int launch_rl_k(const RLArgs& A, cudaStream_t st) {
 
 }  // namespace mvf
 #include "rl_pair.cuh"
+#include "rl_stream.cuh"
 namespace mvf {
 
 // MVF_RL_KERNEL=v2 selects the FFMA2 plane-pair kernel (rl_pair.cuh) for PSFs up to 19 taps; the default is the
@@ -436,6 +437,34 @@ static int launch_rl(int kp, const RLArgs& A, cudaStream_t st) {
     case 31: return launch_rl_k<31, MODE, 2>(A, st);
     case 37: return launch_rl_k<37, MODE, 2>(A, st);
     case 43: return launch_rl_k<43, MODE, 2>(A, st);
+    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 43 taps");
+  }
+}
+
+// streaming two-kernel formulation (rl_stream.cuh): CW = 4 columns per thread up to 19 taps, 2 beyond
+static int launch_rl_xy(int kp, const RLArgs& A, int nplanes, cudaStream_t st) {
+  switch (kp) {
+    case 7: return launch_rl_xy_k<7, 4>(A, nplanes, st);
+    case 13: return launch_rl_xy_k<13, 4>(A, nplanes, st);
+    case 19: return launch_rl_xy_k<19, 4>(A, nplanes, st);
+    case 25: return launch_rl_xy_k<25, 2>(A, nplanes, st);
+    case 31: return launch_rl_xy_k<31, 2>(A, nplanes, st);
+    case 37: return launch_rl_xy_k<37, 2>(A, nplanes, st);
+    case 43: return launch_rl_xy_k<43, 2>(A, nplanes, st);
+    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 43 taps");
+  }
+}
+
+template <int MODE>
+static int launch_rl_z(int kp, const RLArgs& A, cudaStream_t st) {
+  switch (kp) {
+    case 7: return launch_rl_z_k<7, MODE, 4>(A, st);
+    case 13: return launch_rl_z_k<13, MODE, 4>(A, st);
+    case 19: return launch_rl_z_k<19, MODE, 4>(A, st);
+    case 25: return launch_rl_z_k<25, MODE, 2>(A, st);
+    case 31: return launch_rl_z_k<31, MODE, 2>(A, st);
+    case 37: return launch_rl_z_k<37, MODE, 2>(A, st);
+    case 43: return launch_rl_z_k<43, MODE, 2>(A, st);
     default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 43 taps");
   }
 }
@@ -535,4 +564,69 @@ extern "C" int mvf_rl_init_estimate(int nviews, const void* const* host_view_ptr
   rl_init_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(A);
   MVF_LAUNCHED();
   return MVF_OK;
+}
+
+// ---- streaming formulation: x/y passes of all planes, then z pass + epilogue ---------------------------------
+extern "C" int mvf_rl_stream_supported(const int32_t dims[3], const mvf_rl_psf* psf) {
+  if (!dims || !psf || psf->dense) return 0;
+  int kmax = 0;
+  for (int d = 0; d < 3; ++d) kmax = psf->ksize[d] > kmax ? psf->ksize[d] : kmax;
+  const int kp = padded_size(kmax);
+  if (kp < 0) return 0;
+  const int cw = kp <= 19 ? 4 : 2, lead = ((kp - 1) / 2 + cw - 1) / cw * cw;
+  return dims[2] % cw == 0 && dims[2] >= 2 * lead + cw;
+}
+
+extern "C" int mvf_rl_xy(const float* in, int32_t nplanes, const int32_t dims[3], const mvf_rl_psf* psf, float* out,
+                         void* stream) {
+  RLArgs A;
+  int kp;
+  const int32_t zm_dummy = 0;
+  int rc = fill_rl(A, in, &zm_dummy, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(out && nplanes > 0 && nplanes <= 65535, "NULL out or bad plane count");
+  MVF_CHECK_ARG(!psf->dense, "the streaming kernels need a separable PSF");
+  A.out = out;
+  MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2), "rows must be 16-byte aligned (nx % 4 == 0; nx % 2 beyond 19 taps)");
+  return launch_rl_xy(kp, A, nplanes, as_stream(stream));
+}
+
+extern "C" int mvf_rl_blur_z(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                             float* out, void* stream) {
+  RLArgs A;
+  int kp;
+  int rc = fill_rl(A, in, zmap, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(out, "NULL out");
+  A.out = out;
+  MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2), "buffers must be 16-byte aligned and nx a multiple of the vector width");
+  return launch_rl_z<RL_PLAIN>(kp, A, as_stream(stream));
+}
+
+extern "C" int mvf_rl_ratio_z(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                              const void* view, int dtype, const float* weights, float* ratio_out, void* stream) {
+  RLArgs A;
+  int kp;
+  int rc = fill_rl(A, in, zmap, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(view && weights && ratio_out, "NULL argument");
+  MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
+  A.view = view; A.view_u16 = dtype == MVF_U16; A.weights = weights; A.out = ratio_out;
+  MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2, view, weights), "buffers must be 16-byte aligned and nx a multiple of the vector width");
+  return launch_rl_z<RL_RATIO>(kp, A, as_stream(stream));
+}
+
+extern "C" int mvf_rl_correct_z(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
+                                const float* weights, float* corr, int first, int last, float* est,
+                                int64_t est_offset, double* sum_out, void* stream) {
+  RLArgs A;
+  int kp;
+  int rc = fill_rl(A, in, zmap, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(weights && corr, "NULL argument");
+  MVF_CHECK_ARG(!last || est, "est must be given for the last view");
+  A.weights = weights; A.out = corr; A.first = first; A.last = last; A.est = est; A.est_off = est_offset; A.sum = sum_out;
+  MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2, weights, est ? est + est_offset : nullptr),
+                "buffers must be 16-byte aligned and nx a multiple of the vector width");
+  return launch_rl_z<RL_CORRECT>(kp, A, as_stream(stream));
 }

@@ -93,6 +93,12 @@ class FftBlur:
             pass
 
 
+def stream_mode():
+    """Separable blurs run as two streaming kernels (x/y passes of all planes, then z pass + epilogue) unless
+    MVF_RL_KERNEL selects the fused single-kernel variants (v1: scalar FFMA, v2: FFMA2 plane pairs)."""
+    return os.environ.get("MVF_RL_KERNEL", "v3") not in ("v1", "v2", "1", "2")
+
+
 def make_psf_struct(factors):
     s = _cabi.MvfRlPsf()
     for name, k in zip(("kz", "ky", "kx"), factors):
@@ -163,6 +169,9 @@ class RLPlan:
         self._vp = (C.c_void_p * self.n)(*[v.data_ptr() for v in views])
         self._wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in weights])
         self._dims = _cabi.i32x3(self.dims)
+        self.streamed = [sep and stream_mode() and bool(self.lib.mvf_rl_stream_supported(self._dims, C.byref(ps)))
+                         for sep, ps in zip(self.separable, self.psf_structs)]
+        self.tmp = torch.empty(self.dims, dtype=torch.float32, device=dev) if any(self.streamed) else None
 
     def init_estimate(self):
         self.sums.zero_()
@@ -184,6 +193,17 @@ class RLPlan:
                               sums=self.sums[1:])
                 continue
             zm = C.c_void_p(self.zmaps[v].data_ptr())
+            if self.streamed[v]:  # x/y passes of every plane into tmp, then z pass + epilogue
+                ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp.data_ptr())
+                _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est.data_ptr()), self.dims[0], self._dims, ps, tmp, st))
+                _cabi.check(self.lib.mvf_rl_ratio_z(tmp, zm, self._dims, ps, C.c_void_p(self.views[v].data_ptr()),
+                                                    dtype_code(self.views[v]), C.c_void_p(self.weights[v].data_ptr()),
+                                                    C.c_void_p(self.ratio.data_ptr()), st))
+                _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.ratio.data_ptr()), self.dims[0], self._dims, ps, tmp, st))
+                _cabi.check(self.lib.mvf_rl_correct_z(tmp, zm, self._dims, ps, C.c_void_p(self.weights[v].data_ptr()),
+                                                      C.c_void_p(self.corr.data_ptr()), 1 if v == 0 else 0, 1 if last else 0,
+                                                      C.c_void_p(self.est.data_ptr()), 0, C.c_void_p(self.sums[1:].data_ptr()), st))
+                continue
             _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est.data_ptr()), zm, self._dims, C.byref(self.psf_structs[v]),
                                               C.c_void_p(self.views[v].data_ptr()), dtype_code(self.views[v]),
                                               C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.ratio.data_ptr()), st))
@@ -222,6 +242,13 @@ def blur(volume, psf_factors):
     zm = torch.from_numpy(zmap_whole(dims[0], len(psf_factors[0]), padded_radius(psf_factors))).to(volume.device)
     out = torch.empty_like(volume)
     ps = make_psf_struct(psf_factors)
+    if stream_mode() and lib.mvf_rl_stream_supported(_cabi.i32x3(dims), C.byref(ps)):
+        tmp = torch.empty_like(volume)
+        _cabi.check(lib.mvf_rl_xy(C.c_void_p(volume.data_ptr()), dims[0], _cabi.i32x3(dims), C.byref(ps),
+                                  C.c_void_p(tmp.data_ptr()), _stream_ptr()))
+        _cabi.check(lib.mvf_rl_blur_z(C.c_void_p(tmp.data_ptr()), C.c_void_p(zm.data_ptr()), _cabi.i32x3(dims), C.byref(ps),
+                                      C.c_void_p(out.data_ptr()), _stream_ptr()))
+        return out
     _cabi.check(lib.mvf_rl_blur(C.c_void_p(volume.data_ptr()), C.c_void_p(zm.data_ptr()), _cabi.i32x3(dims), C.byref(ps),
                                 C.c_void_p(out.data_ptr()), _stream_ptr()))
     return out
@@ -280,6 +307,10 @@ class SlabRLPlan:
         self._wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in weights])
         self._dims = _cabi.i32x3(self.dims)
         self._est_off = rp * ny * nx
+        self.streamed = [sp is None and not bool(ps.dense) and stream_mode() and
+                         bool(self.lib.mvf_rl_stream_supported(self._dims, C.byref(ps)))
+                         for sp, ps in zip(self.spectra, self.psf_structs)]
+        self.tmp_pad = torch.empty_like(self.est_pad) if any(self.streamed) else None
 
     def init_estimate(self):
         self.sums.zero_()
@@ -293,6 +324,15 @@ class SlabRLPlan:
             self.fft.blur(self.est_pad, self.zmap, self.rp, self.spectra[v], 1, view=self.views[v],
                           weights=self.weights[v], out=self.ratio)
             return
+        if self.streamed[v]:
+            ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp_pad.data_ptr())
+            _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est_pad.data_ptr()), int(self.est_pad.shape[0]), self._dims, ps, tmp,
+                                           _stream_ptr()))
+            _cabi.check(self.lib.mvf_rl_ratio_z(tmp, C.c_void_p(self.zmap.data_ptr()), self._dims, ps,
+                                                C.c_void_p(self.views[v].data_ptr()), dtype_code(self.views[v]),
+                                                C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.ratio.data_ptr()),
+                                                _stream_ptr()))
+            return
         _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
                                           C.byref(self.psf_structs[v]), C.c_void_p(self.views[v].data_ptr()),
                                           dtype_code(self.views[v]), C.c_void_p(self.weights[v].data_ptr()),
@@ -305,6 +345,15 @@ class SlabRLPlan:
             self.fft.blur(self.ratio_pad, self.zmap, self.rp, self.spectra[v], 2, weights=self.weights[v], out=self.corr,
                           first=1 if v == 0 else 0, last=1 if last else 0, est=self.est_pad, est_off=self._est_off,
                           sums=self.sums[1:])
+            return
+        if self.streamed[v]:
+            ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp_pad.data_ptr())
+            _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.ratio_pad.data_ptr()), int(self.ratio_pad.shape[0]), self._dims, ps, tmp,
+                                           _stream_ptr()))
+            _cabi.check(self.lib.mvf_rl_correct_z(tmp, C.c_void_p(self.zmap.data_ptr()), self._dims, ps,
+                                                  C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.corr.data_ptr()),
+                                                  1 if v == 0 else 0, 1 if last else 0, C.c_void_p(self.est_pad.data_ptr()),
+                                                  self._est_off, C.c_void_p(self.sums[1:].data_ptr()), _stream_ptr()))
             return
         _cabi.check(self.lib.mvf_rl_correct(C.c_void_p(self.ratio_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
                                             C.byref(self.psf_structs[v]), C.c_void_p(self.weights[v].data_ptr()),

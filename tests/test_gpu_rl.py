@@ -16,7 +16,7 @@ def _axis_case(shape=(48, 40, 56), nviews=2, seed=5):
     return tv, w, params, sp
 
 
-@pytest.mark.parametrize("kernel", ["v1", "v2"])   # v2: FFMA2 plane-pair kernel (opt-in, PSFs up to 19 taps)
+@pytest.mark.parametrize("kernel", ["v1", "v2", "v3"])   # v1 fused scalar, v2 fused FFMA2 pairs (<= 19 taps), v3 streaming (default)
 @pytest.mark.parametrize("ksize", [(7, 7, 7), (19, 19, 19), (5, 9, 13), (25, 25, 25), (37, 37, 37), (9, 31, 43)])
 def test_blur_matches_closed_form(cuda, ksize, kernel, monkeypatch):
     import torch
@@ -25,7 +25,7 @@ def test_blur_matches_closed_form(cuda, ksize, kernel, monkeypatch):
         pytest.skip("pair kernel covers PSFs up to 19 taps")
     monkeypatch.setenv("MVF_RL_KERNEL", kernel)
     rng = np.random.default_rng(1)
-    x = rng.random((48, 50, 70)).astype(np.float32) * 100
+    x = rng.random((48, 50, 72)).astype(np.float32) * 100   # nx % 4 == 0: every kernel family applies
     f = [np.exp(-0.5 * ((np.arange(k) - k // 2) / (0.15 * k + 0.5)) ** 2).astype(np.float32) for k in ksize]
     f = [(a / a.sum()).astype(np.float32) for a in f]
     f[0][0] *= 1.3  # asymmetric taps: catches a flipped kernel
@@ -100,7 +100,7 @@ def test_rl_oblique_views_dense_psf(cuda, dense_mode, monkeypatch):
     assert float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0))) <= 1e-3
 
 
-@pytest.mark.parametrize("kernel", ["v1", "v2"])
+@pytest.mark.parametrize("kernel", ["v1", "v2", "v3"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_rl_slab_sharded_equals_whole(cuda, world, kernel, monkeypatch):
     """z-slab sharded RL (ranks emulated on one GPU, same kernels, same halo plane movement as the NCCL ring)

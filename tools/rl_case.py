@@ -17,5 +17,9 @@ if os.environ.get("RL_OBLIQUE"):
 plan = rl.RLPlan(views, w, [psf] * V)
 plan.init_estimate(); plan.iterate(); torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record(); plan.iterate(); plan.iterate(); b.record(); torch.cuda.synchronize()
-print("ms/iteration", a.elapsed_time(b) / 2)
+n_it = int(os.environ.get("RL_ITERS", "2"))
+a.record()
+for _ in range(n_it):
+    plan.iterate()
+b.record(); torch.cuda.synchronize()
+print("ms/iteration", a.elapsed_time(b) / n_it)
