@@ -35,9 +35,17 @@ template <int CW> __device__ __forceinline__ void vec_store(float* p, const floa
   else *reinterpret_cast<V*>(p) = make_float2(v[0], v[1]);
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 constexpr int RLS_NT = 256;
-constexpr int RLS_AHEAD = 6;   // rows / planes the L2 prefetch runs ahead of the loads
+#ifndef MVF_RLS_AHEAD
+#define MVF_RLS_AHEAD 6
+#endif
+#ifndef MVF_RLS_NEAR
+#define MVF_RLS_NEAR 0
+#endif
+constexpr int RLS_AHEAD = MVF_RLS_AHEAD;   // rows / planes the L2 prefetch runs ahead of the loads
+constexpr int RLS_NEAR = MVF_RLS_NEAR;     // rows / planes the L1 prefetch runs ahead (0: off)
 
 // ---- x and y passes of every plane -------------------------------------------------------------------------
 template <int K, int CW>
@@ -61,17 +69,22 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_xy_kernel(const __grid_constant_
 #pragma unroll
     for (int m = 0; m < K - 1; ++m) S[i][m] = 0.f;
 
-  for (int t = yo0 - R; t < yo1 + R; ++t) {
-    const float* __restrict__ row = src + (size_t)ext_index(t, A.ny, A.ksz_y) * A.nx;
-    if (t + RLS_AHEAD < yo1 + R) prefetch_l2(src + (size_t)ext_index(t + RLS_AHEAD, A.ny, A.ksz_y) * A.nx + x0);
-    float win[NCH * CW];
+  // Software pipeline: the window of row t+1 is requested right after the x pass of row t has consumed the window
+  // registers, so the loads have the whole y pass (CW * K FFMA) to land.
+  float win[NCH * CW];
+  auto load_window = [&](int t) {
+    const float* __restrict__ row = src + (size_t)ext_index(t, A.ny, A.ksz_y) * A.nx + (xw - LEAD);
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       float v[CW];
-      vec_load<CW>(row + xw - LEAD + j * CW, v);
+      vec_load<CW>(row + j * CW, v);
 #pragma unroll
       for (int i = 0; i < CW; ++i) win[j * CW + i] = v[i];
     }
+  };
+  load_window(yo0 - R);
+  for (int t = yo0 - R; t < yo1 + R; ++t) {
+    if (RLS_AHEAD > 0 && t + RLS_AHEAD < yo1 + R) prefetch_l2(src + (size_t)ext_index(t + RLS_AHEAD, A.ny, A.ksz_y) * A.nx + x0);
     float o[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) o[i] = 0.f;
@@ -81,6 +94,7 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_xy_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < CW; ++i) o[i] = fmaf(kj, win[LEAD + i + R - j], o[i]);
     }
+    if (t + 1 < yo1 + R) load_window(t + 1);
     float e[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -148,11 +162,39 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_z_kernel(const __grid_constant__
   float* __restrict__ est = A.est ? A.est + A.est_off : nullptr;
   double local_sum = 0.0;
 
+  // Software pipeline: the input plane of step t+1 is requested before the multiply-adds of step t (one extra
+  // vector of registers), the epilogue operands of step t+1 right after the epilogue of step t has consumed theirs.
+  float p[CW], pn[CW];
+  float eW[CW], eC[CW], eI[CW];
+  unsigned eRaw[2] = {0u, 0u};   // uint16 view voxels stay packed until they are used
+  auto load_operands = [&](int z) {
+    const size_t o = (size_t)z * plane + i0;
+    vec_load<CW>(wts + o, eW);
+    if (MODE == RL_RATIO) {
+      if (A.view_u16) {
+        const uint16_t* vp = reinterpret_cast<const uint16_t*>(A.view) + o;
+        if constexpr (CW == 4) {
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(vp));
+          eRaw[0] = q.x; eRaw[1] = q.y;
+        } else {
+          eRaw[0] = __ldg(reinterpret_cast<const unsigned*>(vp));
+        }
+      } else {
+        vec_load<CW>(reinterpret_cast<const float*>(A.view) + o, eI);
+      }
+    }
+    if (MODE == RL_CORRECT) {
+      if (!A.first) vec_load<CW>(outp + o, eC);
+      if (A.last) vec_load<CW>(est + o, eI);
+    }
+  };
+  vec_load<CW>(A.in + (size_t)__ldg(zmap + zo0 - R) * plane + i0, pn);
+  if (MODE != RL_PLAIN && R == 0) load_operands(zo0);
   for (int t = zo0 - R; t < zo1 + R; ++t) {
     const int z = t - R;
     const bool emit = z >= zo0;
     const size_t o = (size_t)z * plane + i0;
-    if (t + RLS_AHEAD < zo1 + R) {
+    if (RLS_AHEAD > 0 && t + RLS_AHEAD < zo1 + R) {
       prefetch_l2(A.in + (size_t)__ldg(zmap + t + RLS_AHEAD) * plane + i0);
       if (MODE != RL_PLAIN && z + RLS_AHEAD >= zo0) {   // epilogue operands of the plane completed RLS_AHEAD steps from now
         const size_t oa = o + (size_t)RLS_AHEAD * plane;
@@ -162,32 +204,9 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_z_kernel(const __grid_constant__
         if (MODE == RL_CORRECT && A.last) prefetch_l2(est + oa);
       }
     }
-    float p[CW];
-    vec_load<CW>(A.in + (size_t)__ldg(zmap + t) * plane + i0, p);
-    // epilogue operands of the plane this step completes: requested before the multiply-adds
-    float eW[CW], eC[CW], eI[CW];
-    if (MODE != RL_PLAIN && emit) {
-      vec_load<CW>(wts + o, eW);
-      if (MODE == RL_RATIO) {
-        if (A.view_u16) {
-          const uint16_t* vp = reinterpret_cast<const uint16_t*>(A.view) + o;
-          if constexpr (CW == 4) {
-            const uint2 q = __ldg(reinterpret_cast<const uint2*>(vp));
-            eI[0] = u16_to_float(q.x & 0xFFFFu); eI[1] = u16_to_float(q.x >> 16);
-            eI[2] = u16_to_float(q.y & 0xFFFFu); eI[3] = u16_to_float(q.y >> 16);
-          } else {
-            const unsigned q = __ldg(reinterpret_cast<const unsigned*>(vp));
-            eI[0] = u16_to_float(q & 0xFFFFu); eI[1] = u16_to_float(q >> 16);
-          }
-        } else {
-          vec_load<CW>(reinterpret_cast<const float*>(A.view) + o, eI);
-        }
-      }
-      if (MODE == RL_CORRECT) {
-        if (!A.first) vec_load<CW>(outp + o, eC);
-        if (A.last) vec_load<CW>(est + o, eI);
-      }
-    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) p[i] = pn[i];
+    if (t + 1 < zo1 + R) vec_load<CW>(A.in + (size_t)__ldg(zmap + t + 1) * plane + i0, pn);
     float e[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -197,6 +216,14 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_z_kernel(const __grid_constant__
       S[i][K - 2] = A.kz[K - 1] * p[i];
     }
     if (emit) {
+      if (MODE == RL_RATIO && A.view_u16) {
+        if constexpr (CW == 4) {
+          eI[0] = u16_to_float(eRaw[0] & 0xFFFFu); eI[1] = u16_to_float(eRaw[0] >> 16);
+          eI[2] = u16_to_float(eRaw[1] & 0xFFFFu); eI[3] = u16_to_float(eRaw[1] >> 16);
+        } else {
+          eI[0] = u16_to_float(eRaw[0] & 0xFFFFu); eI[1] = u16_to_float(eRaw[0] >> 16);
+        }
+      }
       float r[CW];
 #pragma unroll
       for (int i = 0; i < CW; ++i) {
@@ -219,6 +246,8 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_z_kernel(const __grid_constant__
       }
       vec_store<CW>((MODE == RL_CORRECT && A.last) ? est + o : outp + o, r);
     }
+    // operands of the plane the next step completes
+    if (MODE != RL_PLAIN && z + 1 >= zo0 && z + 1 < zo1) load_operands(z + 1);
   }
   if (MODE == RL_CORRECT && A.last && A.sum) {
 #pragma unroll
