@@ -129,7 +129,7 @@ def run_rl(dev, rank=0, world=1):
     transformed views and blending weights produced by the fusion kernels.  Returns the `rl` JSON object."""
     import torch
     import torch.nn.functional as F
-    from mvregfus_b200 import fusion, rl, synthetic
+    from mvregfus_b200 import _cabi, fusion, rl, synthetic
     from mvregfus_b200 import multiview as mv
     shape = RL_SHAPE
     g = torch.Generator(device=dev)
@@ -175,11 +175,13 @@ def run_rl(dev, rank=0, world=1):
         dist.barrier()
         torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _cabi.launch_count(reset=True)
     a.record()
     for _ in range(RL_ITERS):
         plan.iterate()
     b.record()
     torch.cuda.synchronize()
+    rl_launches = _cabi.launch_count()
     ms = a.elapsed_time(b)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -192,7 +194,11 @@ def run_rl(dev, rank=0, world=1):
     return {"metric": "rl_iterations_per_s", "value": 1e3 / per_it, "unit": "it/s", "ms_per_iteration": per_it,
             "config": {"workload": "BASELINE.json configs[3]: %d views %dx%dx%d uint16 in the fused frame, Gaussian PSF "
                                    "sigma z=%g xy=%g (19^3, separable), %d iterations" % (NVIEWS, *shape, *RL_SIGMA, RL_ITERS)},
-            "kernel_launches_per_iteration": 2 * NVIEWS, "n_gpus": world,
+            "kernel_launches_per_iteration": rl_launches // RL_ITERS,
+            "kernels": "per view and blur: rl_xy_kernel (x/y passes of every plane) + rl_xy_edge_kernel + rl_z_kernel "
+                       "(z pass + fused ratio / correction / update epilogue)" if getattr(plan, "streamed", [False])[0]
+                       else "rl_blur_kernel (fused x/y/z + epilogue)",
+            "n_gpus": world,
             "sharding": "whole volume" if world == 1 else "z-slabs, ring halo exchange (%d planes) over NCCL before every blur, strong scaling" % ((19 - 1) // 2),
             "roofline": {"bound": "hbm", "achieved": alg / (per_it * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                          "frac": alg / (per_it * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes_per_iteration": alg,

@@ -111,12 +111,11 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_xy_kernel(const __grid_constant_
 // The 2 * LEAD columns next to the x borders of every row: thread = column, index-mapped scalar window (the K source
 // columns of a thread are loop invariant and live in registers), same y shift register.  ~5 % of the main kernel.
 template <int K, int CW>
-__global__ void __launch_bounds__(128) rl_xy_edge_kernel(const __grid_constant__ RLArgs A) {
+__global__ void __launch_bounds__(64) rl_xy_edge_kernel(const __grid_constant__ RLArgs A) {
   constexpr int R = (K - 1) / 2;
   constexpr int LEAD = (R + CW - 1) / CW * CW;
-  const int lane = threadIdx.x & 63, sub = threadIdx.x >> 6;   // 64 threads per (plane, y chunk): 2 * LEAD <= 44 columns
-  const int chunk = blockIdx.y * 2 + sub;
-  const int yo0 = chunk * A.zchunk, yo1 = min(A.ny, yo0 + A.zchunk);
+  const int lane = threadIdx.x;   // one small CTA (32 or 64 threads >= 2 * LEAD columns) per (plane, y chunk): many resident CTAs
+  const int yo0 = blockIdx.y * A.zchunk, yo1 = min(A.ny, yo0 + A.zchunk);
   if (yo0 >= A.ny || lane >= 2 * LEAD) return;
   const int x = lane < LEAD ? lane : A.nx - 2 * LEAD + lane;
   if (x < 0 || x >= A.nx) return;
@@ -129,11 +128,22 @@ __global__ void __launch_bounds__(128) rl_xy_edge_kernel(const __grid_constant__
   float S[K - 1];
 #pragma unroll
   for (int m = 0; m < K - 1; ++m) S[m] = 0.f;
+  float w[K];   // window of the current row; the next row's is requested as soon as the x pass has consumed it
+  {
+    const float* __restrict__ row = src + (size_t)ext_index(yo0 - R, A.ny, A.ksz_y) * A.nx;
+#pragma unroll
+    for (int j = 0; j < K; ++j) w[j] = __ldg(row + col[j]);
+  }
   for (int t = yo0 - R; t < yo1 + R; ++t) {
-    const float* __restrict__ row = src + (size_t)ext_index(t, A.ny, A.ksz_y) * A.nx;
+    if (t + 8 < yo1 + R) prefetch_l2(src + (size_t)ext_index(t + 8, A.ny, A.ksz_y) * A.nx + x);   // the row's two border lines
     float o = 0.f;
 #pragma unroll
-    for (int j = 0; j < K; ++j) o = fmaf(A.kx[j], __ldg(row + col[j]), o);   // same tap order as the main kernel
+    for (int j = 0; j < K; ++j) o = fmaf(A.kx[j], w[j], o);   // same tap order as the main kernel
+    if (t + 1 < yo1 + R) {
+      const float* __restrict__ row = src + (size_t)ext_index(t + 1, A.ny, A.ksz_y) * A.nx;
+#pragma unroll
+      for (int j = 0; j < K; ++j) w[j] = __ldg(row + col[j]);
+    }
     const float e = fmaf(A.ky[0], o, S[0]);
 #pragma unroll
     for (int m = 0; m < K - 2; ++m) S[m] = fmaf(A.ky[m + 1], o, S[m + 1]);
@@ -282,8 +292,9 @@ static int launch_rl_xy_k(RLArgs A, int nplanes, cudaStream_t st) {
   rl_xy_kernel<K, CW><<<grid, RLS_NT, 0, st>>>(A);
   MVF_LAUNCHED();
   A.zchunk = A.ny < 64 ? A.ny : 64;   // short y chunks: the edge columns are few, parallelism comes from the chunks
-  dim3 egrid(1, ((A.ny + A.zchunk - 1) / A.zchunk + 1) / 2, nplanes);
-  rl_xy_edge_kernel<K, CW><<<egrid, 128, 0, st>>>(A);
+  constexpr int ELEAD = ((K - 1) / 2 + CW - 1) / CW * CW;
+  dim3 egrid(1, (A.ny + A.zchunk - 1) / A.zchunk, nplanes);
+  rl_xy_edge_kernel<K, CW><<<egrid, 2 * ELEAD <= 32 ? 32 : 64, 0, st>>>(A);
   MVF_LAUNCHED();
   return MVF_OK;
 }
