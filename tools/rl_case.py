@@ -8,8 +8,10 @@ V = 4
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 views = [(torch.rand(shape, generator=g, device="cuda") * 3000).to(torch.int32).to(torch.uint16) for _ in range(V)]
 w = [torch.full(shape, 1.0 / V, device="cuda") for _ in range(V)]
-k = np.exp(-0.5 * (np.arange(-9, 10) / 6.0) ** 2); kz = (k / k.sum()).astype(np.float32)
-k = np.exp(-0.5 * (np.arange(-9, 10) / 2.0) ** 2); kxy = (k / k.sum()).astype(np.float32)
+Rk = (int(os.environ.get("RL_K", "19")) - 1) // 2   # RL_K=37: the PSF of BASELINE configs[4] (spacing 0.5)
+sc = Rk / 9.0
+k = np.exp(-0.5 * (np.arange(-Rk, Rk + 1) / (6.0 * sc)) ** 2); kz = (k / k.sum()).astype(np.float32)
+k = np.exp(-0.5 * (np.arange(-Rk, Rk + 1) / (2.0 * sc)) ** 2); kxy = (k / k.sum()).astype(np.float32)
 psf = kz[:, None, None] * kxy[None, :, None] * kxy[None, None, :]
 if os.environ.get("RL_OBLIQUE"):
     from scipy import ndimage
