@@ -72,19 +72,27 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_xy_kernel(const __grid_constant_
   // Software pipeline: the window of row t+1 is requested right after the x pass of row t has consumed the window
   // registers, so the loads have the whole y pass (CW * K FFMA) to land.
   float win[NCH * CW];
-  auto load_window = [&](int t) {
-    const float* __restrict__ row = src + (size_t)ext_index(t, A.ny, A.ksz_y) * A.nx + (xw - LEAD);
+  // Row pointers advance by nx inside the volume; only rows that go through the index map (t < 0 or t >= ny, i.e.
+  // the ramps at the volume borders) pay for ext_index.
+  auto row_ptr = [&](int t) { return src + (size_t)ext_index(t, A.ny, A.ksz_y) * A.nx; };
+  auto load_window = [&](const float* __restrict__ rowp) {
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       float v[CW];
-      vec_load<CW>(row + j * CW, v);
+      vec_load<CW>(rowp + (xw - LEAD) + j * CW, v);
 #pragma unroll
       for (int i = 0; i < CW; ++i) win[j * CW + i] = v[i];
     }
   };
-  load_window(yo0 - R);
+  const float* __restrict__ cur = row_ptr(yo0 - R);                 // row t
+  const float* __restrict__ far = row_ptr(yo0 - R + RLS_AHEAD);     // row t + RLS_AHEAD (L2 prefetch)
+  load_window(cur);
   for (int t = yo0 - R; t < yo1 + R; ++t) {
-    if (RLS_AHEAD > 0 && t + RLS_AHEAD < yo1 + R) prefetch_l2(src + (size_t)ext_index(t + RLS_AHEAD, A.ny, A.ksz_y) * A.nx + x0);
+    if (RLS_AHEAD > 0 && t + RLS_AHEAD < yo1 + R) prefetch_l2(far + x0);
+    {
+      const int tf = t + RLS_AHEAD + 1;
+      far = (tf >= 1 && tf < A.ny) ? far + A.nx : row_ptr(tf);
+    }
     float o[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) o[i] = 0.f;
@@ -94,7 +102,8 @@ __global__ void __launch_bounds__(RLS_NT, 2) rl_xy_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < CW; ++i) o[i] = fmaf(kj, win[LEAD + i + R - j], o[i]);
     }
-    if (t + 1 < yo1 + R) load_window(t + 1);
+    cur = (t + 1 >= 1 && t + 1 < A.ny) ? cur + A.nx : row_ptr(t + 1);
+    if (t + 1 < yo1 + R) load_window(cur);
     float e[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
