@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from scipy import ndimage, optimize
 
-from . import _cabi, fusion
+from . import _cabi, _host_workers, _hostpool, fusion
 
 CHUNK = 128  # the reference's fusion chunk size (mv:3716)
 
@@ -86,10 +86,13 @@ def quality_grid(tviews, params, orig_stack_propertiess, stack_properties):
     qspacing = spacing * b
     # which views see which block (2^3 probe points, bit-exact host arithmetic)
     inside = np.zeros((nv,) + tuple(nb), dtype=np.int64)
-    for loc in np.ndindex(*nb):
-        origin = np.array([stack_properties["origin"][i] + loc[i] * size * qspacing[i] for i in range(3)])
-        bprops = {"size": np.array([size] * 3).astype(np.int64), "spacing": np.array(qspacing), "origin": origin}
-        inside[(slice(None),) + loc] = fusion.blocks_inside_codes(orig_stack_propertiess, params, bprops, 2)
+    locs = list(np.ndindex(*nb))
+    props_np = [{k: np.asarray(v) for k, v in osp.items()} for osp in orig_stack_propertiess]
+    tasks = [(locs[a:b2], np.asarray(stack_properties["origin"], dtype=np.float64), size, np.array(qspacing), props_np,
+              np.asarray(params, dtype=np.float64)) for a, b2 in _hostpool.chunks(len(locs))]
+    codes = np.concatenate(_hostpool.pmap(_host_workers.block_codes_chunk, tasks, min_tasks=2 if len(locs) >= 256 else 10 ** 9))
+    for n, loc in enumerate(locs):
+        inside[(slice(None),) + loc] = codes[n]
     seen = inside > 0
     nseen = seen.sum(0)
     ws = np.full((nv,) + tuple(nb), np.nan, dtype=np.float64)
@@ -107,27 +110,7 @@ def quality_grid(tviews, params, orig_stack_propertiess, stack_properties):
     return ws, b, size
 
 
-def _adapt_weights(ws, how_many_best_views, cumulative_weight_best_views):
-    """Exponent fit of one coarse cell (mv:4155-4210)."""
-    wsum = np.sum(ws, 0)
-    if wsum > 0:
-        ws = ws / wsum
-    if not (np.sum(ws > 0) >= 2):
-        return ws
-    wfs = np.sort(ws.astype(np.float64), axis=0)
-
-    def energy(exp):
-        tmpw = wfs ** exp[0]
-        tmpw = tmpw / np.nansum(tmpw, 0)
-        nsum = np.nansum(tmpw[-int(how_many_best_views):], (-1))
-        return np.abs(np.nansum(nsum) - cumulative_weight_best_views)
-
-    res = optimize.minimize(energy, [0.5], bounds=[[0.01, 100]], method='L-BFGS-B', options={'maxiter': 10})
-    ws = np.array([ws[i] ** res.x[0] for i in range(len(ws))])
-    wsum = np.sum(ws, 0)
-    if wsum > 0:
-        ws = ws / wsum
-    return ws
+from ._host_workers import adapt_weights as _adapt_weights  # noqa: E402  (torch-free implementation, shared with the pool)
 
 
 def _nan_gaussian(U, sigma):
@@ -152,10 +135,10 @@ def coarse_weights(ws, stack_properties, b, size, max_kernel=None, how_many_best
     nanmask = np.isnan(ws)
     ws = np.array([ndimage.generic_filter(ws[i], function=np.nanmax, size=int(filter_size)) for i in range(len(ws))])
     ws[nanmask] = 0
-    adapted = np.zeros(ws.shape, dtype=np.float64)
-    for idx in np.ndindex(ws.shape[1:]):
-        sel = (slice(None),) + idx
-        adapted[sel] = _adapt_weights(ws[sel], how_many_best_views, cumulative_weight_best_views)
+    cells = np.ascontiguousarray(ws.reshape(ws.shape[0], -1).T)          # (ncells, V), one row per coarse cell
+    tasks = [(cells[a:b2], how_many_best_views, cumulative_weight_best_views) for a, b2 in _hostpool.chunks(len(cells))]
+    fitted = np.concatenate(_hostpool.pmap(_host_workers.adapt_cells_chunk, tasks, min_tasks=2 if len(cells) >= 256 else 10 ** 9))
+    adapted = np.ascontiguousarray(fitted.T).reshape(ws.shape).astype(np.float64)
     ws = np.array([_nan_gaussian(adapted[i], filter_size / 2.) for i in range(len(adapted))])
     ws[nanmask] = 0
     origin = np.asarray(stack_properties["origin"]) + (spacing * (size * b - 1)) / 2.

@@ -53,27 +53,7 @@ def probe_any_inside(orig_props, p, stack_properties, n_points=5):
     return bool(_probe_flags(orig_props, p, stack_properties, n_points).any())
 
 
-def _probe_flags(orig_props, p, stack_properties, n_points):
-    rel = np.linspace(0, 1, n_points)
-    grid = np.stack(np.meshgrid(rel, rel, rel, indexing="ij"), -1).reshape(-1, 3)
-    p = np.asarray(p, dtype=np.float64)
-    A, c = p[:9].reshape(3, 3), p[9:]
-    flags = np.empty(len(grid), dtype=bool)
-    size = np.asarray(orig_props["size"])
-    for i, g in enumerate(grid):  # same operation order as the reference loop (bit-exact flags)
-        phys = stack_properties["origin"] + np.array(g) * stack_properties["size"] * stack_properties["spacing"]
-        pix = (np.dot(A, phys) + c - orig_props["origin"]) / orig_props["spacing"]
-        flags[i] = bool(np.all((pix >= 0) & (pix < size)))
-    return flags
-
-
-def blocks_inside_codes(orig_stack_propertiess, params, stack_properties, n_points_per_dim=5):
-    """1 all probe points inside / 0 none / 2 partial, per view (mv:3406-3466)."""
-    codes = []
-    for osp, p in zip(orig_stack_propertiess, params):
-        f = _probe_flags(osp, p, stack_properties, n_points_per_dim)
-        codes.append(1 if f.all() else (2 if f.any() else 0))
-    return np.array(codes)
+from ._host_workers import blocks_inside_codes, probe_flags as _probe_flags  # noqa: E402,F401  (torch-free implementation)
 
 
 def border_profiles(orig_props):
