@@ -318,43 +318,69 @@ class SlabRLPlan:
                                                   C.c_void_p(self.est.data_ptr()), self.est.numel(),
                                                   C.c_void_p(self.sums.data_ptr()), _stream_ptr()))
 
-    def step_ratio(self, v):
-        """R_v = I_v / (blur(est) + 1e-6) * mask, read from the halo-padded estimate."""
+    def _xy_planes(self, src_pad, v, pending=()):
+        """x/y passes of src_pad into tmp_pad.  With a halo exchange in flight (`pending`) the own planes go first
+        and the halo planes follow once they have arrived, so the transfer runs beside the bulk of the work."""
+        from . import slab
+        ps, st = C.byref(self.psf_structs[v]), _stream_ptr()
+        nzl, rp = self.dims[0], self.rp
+        pstride = self.dims[1] * self.dims[2] * 4
+
+        def run(p0, n):
+            _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(src_pad.data_ptr() + p0 * pstride), int(n), self._dims, ps,
+                                           C.c_void_p(self.tmp_pad.data_ptr() + p0 * pstride), st))
+        if not pending or rp == 0:
+            slab.exchange_halos_end(pending)
+            run(0, nzl + 2 * rp)
+            return
+        run(rp, nzl)
+        slab.exchange_halos_end(pending)
+        run(0, rp)
+        run(rp + nzl, rp)
+
+    def step_ratio(self, v, pending=()):
+        """R_v = I_v / (blur(est) + 1e-6) * mask, read from the halo-padded estimate (`pending`: requests of an
+        estimate halo exchange still in flight)."""
+        from . import slab
         if self.spectra[v] is not None:
+            slab.exchange_halos_end(pending)
             self.fft.blur(self.est_pad, self.zmap, self.rp, self.spectra[v], 1, view=self.views[v],
                           weights=self.weights[v], out=self.ratio)
             return
         if self.streamed[v]:
             ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp_pad.data_ptr())
-            _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est_pad.data_ptr()), int(self.est_pad.shape[0]), self._dims, ps, tmp,
-                                           _stream_ptr()))
+            self._xy_planes(self.est_pad, v, pending)
             _cabi.check(self.lib.mvf_rl_ratio_z(tmp, C.c_void_p(self.zmap.data_ptr()), self._dims, ps,
                                                 C.c_void_p(self.views[v].data_ptr()), dtype_code(self.views[v]),
                                                 C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.ratio.data_ptr()),
                                                 _stream_ptr()))
             return
+        slab.exchange_halos_end(pending)
         _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
                                           C.byref(self.psf_structs[v]), C.c_void_p(self.views[v].data_ptr()),
                                           dtype_code(self.views[v]), C.c_void_p(self.weights[v].data_ptr()),
                                           C.c_void_p(self.ratio.data_ptr()), _stream_ptr()))
 
-    def step_correct(self, v):
-        """C (+)= blur(R_v) * w_v; the last view applies the multiplicative update to the estimate."""
+    def step_correct(self, v, pending=()):
+        """C (+)= blur(R_v) * w_v; the last view applies the multiplicative update to the estimate (`pending`:
+        requests of a ratio halo exchange still in flight)."""
+        from . import slab
         last = v == self.n - 1
         if self.spectra[v] is not None:
+            slab.exchange_halos_end(pending)
             self.fft.blur(self.ratio_pad, self.zmap, self.rp, self.spectra[v], 2, weights=self.weights[v], out=self.corr,
                           first=1 if v == 0 else 0, last=1 if last else 0, est=self.est_pad, est_off=self._est_off,
                           sums=self.sums[1:])
             return
         if self.streamed[v]:
             ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp_pad.data_ptr())
-            _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.ratio_pad.data_ptr()), int(self.ratio_pad.shape[0]), self._dims, ps, tmp,
-                                           _stream_ptr()))
+            self._xy_planes(self.ratio_pad, v, pending)
             _cabi.check(self.lib.mvf_rl_correct_z(tmp, C.c_void_p(self.zmap.data_ptr()), self._dims, ps,
                                                   C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.corr.data_ptr()),
                                                   1 if v == 0 else 0, 1 if last else 0, C.c_void_p(self.est_pad.data_ptr()),
                                                   self._est_off, C.c_void_p(self.sums[1:].data_ptr()), _stream_ptr()))
             return
+        slab.exchange_halos_end(pending)
         _cabi.check(self.lib.mvf_rl_correct(C.c_void_p(self.ratio_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
                                             C.byref(self.psf_structs[v]), C.c_void_p(self.weights[v].data_ptr()),
                                             C.c_void_p(self.corr.data_ptr()), 1 if v == 0 else 0, 1 if last else 0,
@@ -364,11 +390,13 @@ class SlabRLPlan:
     def iterate(self):
         from . import slab
         self.sums[1:].zero_()
-        slab.exchange_halos(self.est_pad, self.halo, self.group)     # one exchange serves all views' first blur
+        # one estimate exchange serves all views' first blur; every exchange runs beside the x/y passes of the own planes
+        pending = slab.exchange_halos_begin(self.est_pad, self.halo, self.group)
         for v in range(self.n):
-            self.step_ratio(v)
-            slab.exchange_halos(self.ratio_pad, self.halo, self.group)
-            self.step_correct(v)
+            self.step_ratio(v, pending)
+            pending = slab.exchange_halos_begin(self.ratio_pad, self.halo, self.group)
+            self.step_correct(v, pending)
+            pending = ()
 
     def run(self, num_iterations=25, tol=5e-5):
         import torch.distributed as dist

@@ -77,12 +77,14 @@ class HaloPlan:
         return np.arange(0, self.rp) if self.rank > 0 else None
 
 
-def exchange_halos(buf, plan, group=None):
-    """Fill the halo planes of `buf` ((nzl+2rp, ny, nx), own planes already written) from the ring neighbours."""
+def exchange_halos_begin(buf, plan, group=None):
+    """Start filling the halo planes of `buf` ((nzl+2rp, ny, nx), own planes already written) from the ring
+    neighbours; returns the pending requests (empty for a single rank).  Work that only touches own planes may be
+    queued before :func:`exchange_halos_end` - with NCCL the transfers then run beside it."""
     import torch.distributed as dist
     rp, nzl = plan.rp, plan.nzl
     if plan.world == 1:
-        return
+        return []
     up_idx = torch.as_tensor(plan.planes_for_upper_neighbour() + rp, device=buf.device, dtype=torch.long)
     send_up = buf.index_select(0, up_idx).contiguous()
     ops = [dist.P2POp(dist.isend, send_up, (plan.rank + 1) % plan.world, group=group),
@@ -92,8 +94,17 @@ def exchange_halos(buf, plan, group=None):
         ops.append(dist.P2POp(dist.isend, send_down, plan.rank - 1, group=group))
     if plan.upper_src is not None:
         ops.append(dist.P2POp(dist.irecv, buf[rp + nzl:rp + nzl + rp], plan.upper_src, group=group))
-    for req in dist.batch_isend_irecv(ops):
+    return list(dist.batch_isend_irecv(ops))
+
+
+def exchange_halos_end(reqs):
+    for req in reqs:
         req.wait()
+
+
+def exchange_halos(buf, plan, group=None):
+    """Blocking form: fill the halo planes of `buf` from the ring neighbours."""
+    exchange_halos_end(exchange_halos_begin(buf, plan, group))
 
 
 def exchange_halos_local(bufs, plans):
