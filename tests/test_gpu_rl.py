@@ -157,3 +157,17 @@ def test_rl_slab_sharded_oblique_fft(cuda):
     got = torch.cat([p.est for p in plans], 0).cpu().numpy()
     # the padded FFT length differs between slab and whole volume: float32 FFT noise, not bit equality
     assert float(np.max(np.abs(got - whole) / np.maximum(np.abs(whole), 1.0))) <= 1e-3
+
+
+@pytest.mark.parametrize("kernel", ["v1", "v3"])
+def test_rl_float32_views_equal_uint16_views(cuda, kernel, monkeypatch):
+    """float32 views holding the same integers take the float operand path of the epilogues: identical estimate."""
+    import torch
+    from mvregfus_b200 import fusion, rl, multiview as mv
+    monkeypatch.setenv("MVF_RL_KERNEL", kernel)
+    tv, w, params, sp = _axis_case(nviews=2)
+    psfs = [mv.get_psf(p, sp, 3, 1) for p in params]
+    dw = [fusion.to_device(x) for x in w]
+    a = rl.RLPlan([fusion.to_device(v) for v in tv], dw, psfs).run(num_iterations=3).clone()
+    b = rl.RLPlan([fusion.to_device(np.asarray(v).astype(np.float32)) for v in tv], dw, psfs).run(num_iterations=3)
+    assert torch.equal(a, b)
