@@ -612,7 +612,9 @@ extern "C" int mvf_rl_ratio_z(const float* in, const int32_t* zmap, const int32_
   MVF_CHECK_ARG(view && weights && ratio_out, "NULL argument");
   MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
   A.view = view; A.view_u16 = dtype == MVF_U16; A.weights = weights; A.out = ratio_out;
-  MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2, view, weights), "buffers must be 16-byte aligned and nx a multiple of the vector width");
+  // a uint16 view moves as 2 * CW bytes per thread: checking it with a doubled address applies the halved requirement
+  const void* view_chk = dtype == MVF_U16 ? reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(view) * 2) : view;
+  MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2, view_chk, weights), "buffers must be 16-byte aligned and nx a multiple of the vector width");
   return launch_rl_z<RL_RATIO>(kp, A, as_stream(stream));
 }
 

@@ -99,6 +99,11 @@ def stream_mode():
     return os.environ.get("MVF_RL_KERNEL", "v3") not in ("v1", "v2", "1", "2")
 
 
+def _vector_aligned(*tensors):
+    """16-byte aligned float32 / 8-byte aligned uint16 buffers: what the vector loads of the streaming kernels need."""
+    return all(t is None or t.data_ptr() % (16 if t.element_size() == 4 else 8) == 0 for t in tensors)
+
+
 def make_psf_struct(factors):
     s = _cabi.MvfRlPsf()
     for name, k in zip(("kz", "ky", "kx"), factors):
@@ -169,8 +174,9 @@ class RLPlan:
         self._vp = (C.c_void_p * self.n)(*[v.data_ptr() for v in views])
         self._wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in weights])
         self._dims = _cabi.i32x3(self.dims)
-        self.streamed = [sep and stream_mode() and bool(self.lib.mvf_rl_stream_supported(self._dims, C.byref(ps)))
-                         for sep, ps in zip(self.separable, self.psf_structs)]
+        self.streamed = [sep and stream_mode() and bool(self.lib.mvf_rl_stream_supported(self._dims, C.byref(ps))) and
+                         _vector_aligned(vw, ww, self.est, self.ratio, self.corr)
+                         for sep, ps, vw, ww in zip(self.separable, self.psf_structs, views, weights)]
         self.tmp = torch.empty(self.dims, dtype=torch.float32, device=dev) if any(self.streamed) else None
 
     def init_estimate(self):
@@ -242,7 +248,7 @@ def blur(volume, psf_factors):
     zm = torch.from_numpy(zmap_whole(dims[0], len(psf_factors[0]), padded_radius(psf_factors))).to(volume.device)
     out = torch.empty_like(volume)
     ps = make_psf_struct(psf_factors)
-    if stream_mode() and lib.mvf_rl_stream_supported(_cabi.i32x3(dims), C.byref(ps)):
+    if stream_mode() and lib.mvf_rl_stream_supported(_cabi.i32x3(dims), C.byref(ps)) and _vector_aligned(volume, out):
         tmp = torch.empty_like(volume)
         _cabi.check(lib.mvf_rl_xy(C.c_void_p(volume.data_ptr()), dims[0], _cabi.i32x3(dims), C.byref(ps),
                                   C.c_void_p(tmp.data_ptr()), _stream_ptr()))
@@ -308,8 +314,9 @@ class SlabRLPlan:
         self._dims = _cabi.i32x3(self.dims)
         self._est_off = rp * ny * nx
         self.streamed = [sp is None and not bool(ps.dense) and stream_mode() and
-                         bool(self.lib.mvf_rl_stream_supported(self._dims, C.byref(ps)))
-                         for sp, ps in zip(self.spectra, self.psf_structs)]
+                         bool(self.lib.mvf_rl_stream_supported(self._dims, C.byref(ps))) and
+                         _vector_aligned(vw, ww, self.est, self.ratio, self.corr)
+                         for sp, ps, vw, ww in zip(self.spectra, self.psf_structs, views, weights)]
         self.tmp_pad = torch.empty_like(self.est_pad) if any(self.streamed) else None
 
     def init_estimate(self):

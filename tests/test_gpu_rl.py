@@ -171,3 +171,26 @@ def test_rl_float32_views_equal_uint16_views(cuda, kernel, monkeypatch):
     a = rl.RLPlan([fusion.to_device(v) for v in tv], dw, psfs).run(num_iterations=3).clone()
     b = rl.RLPlan([fusion.to_device(np.asarray(v).astype(np.float32)) for v in tv], dw, psfs).run(num_iterations=3)
     assert torch.equal(a, b)
+
+
+def test_rl_misaligned_view_falls_back_to_fused_kernel(cuda):
+    """A uint16 view that starts 2 bytes into its allocation cannot feed the 8-byte vector loads of the streaming
+    kernels: the plan must pick the fused kernel for it and still produce the same estimate (to rounding order)."""
+    import torch
+    from mvregfus_b200 import fusion, rl, multiview as mv
+    tv, w, params, sp = _axis_case(nviews=2)
+    psfs = [mv.get_psf(p, sp, 3, 1) for p in params]
+    dv, dw = [fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w]
+    ref_plan = rl.RLPlan(dv, dw, psfs)
+    assert all(ref_plan.streamed)
+    ref = ref_plan.run(num_iterations=3).clone()
+    odd = []
+    for v in dv:
+        buf = torch.empty(v.numel() + 1, dtype=torch.uint16, device=v.device)
+        buf[1:] = v.reshape(-1)
+        odd.append(buf[1:].view(v.shape))
+        assert odd[-1].data_ptr() % 8 == 2
+    plan = rl.RLPlan(odd, dw, psfs)
+    assert not any(plan.streamed)
+    got = plan.run(num_iterations=3)
+    assert float(((got - ref).abs() / ref.abs().clamp_min(1.0)).max()) <= 1e-4
