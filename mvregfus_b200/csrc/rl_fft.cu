@@ -39,24 +39,39 @@ struct GatherArgs {
 };
 
 // padded[p] = ext(p) for p <= n-1+R, ext(p-L) for p >= L-R, else 0 (per axis, separable index map)
+// One CTA per (pz, py) row segment of FFT_XPT * 256 elements: every thread moves FFT_XPT elements (stride 256, all
+// loads issued before the stores), the z / y parts of the index map are computed once per CTA row.
+constexpr int FFT_XPT = 4;
 __global__ void __launch_bounds__(256) fft_gather_kernel(const __grid_constant__ GatherArgs A) {
-  const int px = blockIdx.x * 256 + threadIdx.x;
   const int py = blockIdx.y, pz = blockIdx.z;
-  if (px >= A.L[2]) return;
-  const int p[3] = {pz, py, px};
-  int src[3];
-  bool zero = false;
+  int srow[2];
+  bool zero_row = false;
+  const int pr[2] = {pz, py};
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < 2; ++d) {
     int t;
-    if (p[d] <= A.n[d] - 1 + A.R[d]) t = p[d];
-    else if (p[d] >= A.L[d] - A.R[d]) t = p[d] - A.L[d];
-    else { zero = true; t = 0; }
-    src[d] = d == 0 ? A.zmap[t + A.rp] : ext_index_fft(t, A.n[d], A.K[d]);
+    if (pr[d] <= A.n[d] - 1 + A.R[d]) t = pr[d];
+    else if (pr[d] >= A.L[d] - A.R[d]) t = pr[d] - A.L[d];
+    else { zero_row = true; t = 0; }
+    srow[d] = d == 0 ? A.zmap[t + A.rp] : ext_index_fft(t, A.n[d], A.K[d]);
   }
-  float v = 0.f;
-  if (!zero) v = __ldg(A.in + ((size_t)src[0] * A.n[1] + src[1]) * A.n[2] + src[2]);
-  A.out[((size_t)pz * A.L[1] + py) * A.L[2] + px] = v;
+  const float* __restrict__ src = A.in + ((size_t)srow[0] * A.n[1] + srow[1]) * A.n[2];
+  float* __restrict__ dst = A.out + ((size_t)pz * A.L[1] + py) * A.L[2];
+  float v[FFT_XPT];
+#pragma unroll
+  for (int k = 0; k < FFT_XPT; ++k) {
+    const int px = (blockIdx.x * FFT_XPT + k) * 256 + threadIdx.x;
+    v[k] = 0.f;
+    if (px < A.L[2] && !zero_row) {
+      const bool low = px <= A.n[2] - 1 + A.R[2], high = px >= A.L[2] - A.R[2];
+      if (low || high) v[k] = __ldg(src + ext_index_fft(low ? px : px - A.L[2], A.n[2], A.K[2]));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < FFT_XPT; ++k) {
+    const int px = (blockIdx.x * FFT_XPT + k) * 256 + threadIdx.x;
+    if (px < A.L[2]) dst[px] = v[k];
+  }
 }
 
 __global__ void __launch_bounds__(256) fft_place_psf_kernel(const float* psf, int kz, int ky, int kx, float* out, int Lz, int Ly, int Lx) {
@@ -88,25 +103,44 @@ struct FftEpiArgs {
 
 // out[i] = conv[i + R] cropped (mv:5669), clamped at 0, followed by the same epilogues as the separable kernel
 __global__ void __launch_bounds__(256) fft_epilogue_kernel(const __grid_constant__ FftEpiArgs A) {
-  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+  const int y = blockIdx.y, z = blockIdx.z;
   double local_sum = 0.0;
-  if (x < A.n[2]) {
-    const float blur = fmaxf(A.conv[((size_t)(z + A.R[0]) * A.L[1] + (y + A.R[1])) * A.L[2] + (x + A.R[2])], 0.f);
-    const size_t idx = ((size_t)z * A.n[1] + y) * A.n[2] + x;
+  const float* __restrict__ crow = A.conv + ((size_t)(z + A.R[0]) * A.L[1] + (y + A.R[1])) * A.L[2] + A.R[2];
+  const size_t row = ((size_t)z * A.n[1] + y) * A.n[2];
+  // FFT_XPT elements per thread (stride 256); every operand of all of them is requested before the arithmetic
+  float c[FFT_XPT], w[FFT_XPT], I[FFT_XPT], o[FFT_XPT], e[FFT_XPT];
+#pragma unroll
+  for (int k = 0; k < FFT_XPT; ++k) {
+    const int x = (blockIdx.x * FFT_XPT + k) * 256 + threadIdx.x;
+    c[k] = w[k] = I[k] = o[k] = e[k] = 0.f;
+    if (x < A.n[2]) {
+      const size_t idx = row + x;
+      c[k] = __ldg(crow + x);
+      if (A.mode != 0) w[k] = __ldg(A.weights + idx);
+      if (A.mode == 1) I[k] = A.view_u16 ? u16_to_float(__ldg(reinterpret_cast<const uint16_t*>(A.view) + idx))
+                                         : __ldg(reinterpret_cast<const float*>(A.view) + idx);
+      if (A.mode == 2 && !A.first) o[k] = A.out[idx];
+      if (A.mode == 2 && A.last) e[k] = A.est[A.est_off + idx];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < FFT_XPT; ++k) {
+    const int x = (blockIdx.x * FFT_XPT + k) * 256 + threadIdx.x;
+    if (x >= A.n[2]) continue;
+    const size_t idx = row + x;
+    const float blur = fmaxf(c[k], 0.f);
     if (A.mode == 0) {
       A.out[idx] = blur;
     } else if (A.mode == 1) {
-      const float I = A.view_u16 ? u16_to_float(reinterpret_cast<const uint16_t*>(A.view)[idx])
-                                 : reinterpret_cast<const float*>(A.view)[idx];
-      const float ratio = __fdiv_rn(I, blur + 1e-6f);
-      A.out[idx] = A.weights[idx] > 1e-5f ? ratio : 0.f;
+      const float ratio = __fdiv_rn(I[k], blur + 1e-6f);
+      A.out[idx] = w[k] > 1e-5f ? ratio : 0.f;
     } else {
-      const float o = blur * A.weights[idx];
-      const float corr = A.first ? o : A.out[idx] + o;
+      const float ow = blur * w[k];
+      const float corr = A.first ? ow : o[k] + ow;
       if (A.last) {
-        const float v = fminf(fmaxf(A.est[A.est_off + idx] * corr, 0.f), 65535.f);
+        const float v = fminf(fmaxf(e[k] * corr, 0.f), 65535.f);
         A.est[A.est_off + idx] = v;
-        local_sum = (double)v;
+        local_sum += (double)v;
       } else {
         A.out[idx] = corr;
       }
@@ -114,7 +148,7 @@ __global__ void __launch_bounds__(256) fft_epilogue_kernel(const __grid_constant
   }
   if (A.mode == 2 && A.last && A.sum) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local_sum += __shfl_xor_sync(0xffffffffu, local_sum, o);
+    for (int s = 16; s > 0; s >>= 1) local_sum += __shfl_xor_sync(0xffffffffu, local_sum, s);
     if ((threadIdx.x & 31) == 0 && local_sum != 0.0) atomicAdd(A.sum, local_sum);
   }
 }
@@ -208,7 +242,7 @@ extern "C" int mvf_rl_fft_blur(void* plan, const float* in, const int32_t* zmap,
   GatherArgs G;
   G.in = in; G.zmap = zmap; G.rp = zmap_radius; G.out = real_buf;
   for (int d = 0; d < 3; ++d) { G.n[d] = p->n[d]; G.L[d] = p->L[d]; G.K[d] = ksize[d]; G.R[d] = (ksize[d] - 1) / 2; }
-  fft_gather_kernel<<<dim3((p->L[2] + 255) / 256, p->L[1], p->L[0]), 256, 0, st>>>(G);
+  fft_gather_kernel<<<dim3((p->L[2] + 256 * FFT_XPT - 1) / (256 * FFT_XPT), p->L[1], p->L[0]), 256, 0, st>>>(G);
   MVF_LAUNCHED();
   MVF_CUFFT(cufftSetStream(p->r2c, st));
   MVF_CUFFT(cufftSetStream(p->c2r, st));
@@ -224,7 +258,7 @@ extern "C" int mvf_rl_fft_blur(void* plan, const float* in, const int32_t* zmap,
   E.conv = real_buf; E.mode = mode; E.view = view; E.view_u16 = dtype == MVF_U16; E.weights = weights; E.out = out;
   E.first = first; E.last = last; E.est = est; E.est_off = est_offset; E.sum = sum_out;
   for (int d = 0; d < 3; ++d) { E.n[d] = p->n[d]; E.L[d] = p->L[d]; E.R[d] = (ksize[d] - 1) / 2; }
-  fft_epilogue_kernel<<<dim3((p->n[2] + 255) / 256, p->n[1], p->n[0]), 256, 0, st>>>(E);
+  fft_epilogue_kernel<<<dim3((p->n[2] + 256 * FFT_XPT - 1) / (256 * FFT_XPT), p->n[1], p->n[0]), 256, 0, st>>>(E);
   MVF_LAUNCHED();
   return MVF_OK;
 }
