@@ -37,7 +37,13 @@ template <int CW> __device__ __forceinline__ void vec_store(float* p, const floa
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-constexpr int RLS_NT = 256;
+#ifndef MVF_RLS_NT
+#define MVF_RLS_NT 256
+#endif
+#ifndef MVF_RLS_MINB
+#define MVF_RLS_MINB 2
+#endif
+constexpr int RLS_NT = MVF_RLS_NT;   // threads per CTA of the streaming kernels, MVF_RLS_MINB CTAs per SM
 #ifndef MVF_RLS_AHEAD
 #define MVF_RLS_AHEAD 6
 #endif
@@ -49,7 +55,7 @@ constexpr int RLS_NEAR = MVF_RLS_NEAR;     // rows / planes the L1 prefetch runs
 
 // ---- x and y passes of every plane -------------------------------------------------------------------------
 template <int K, int CW>
-__global__ void __launch_bounds__(RLS_NT, 2) rl_xy_kernel(const __grid_constant__ RLArgs A) {
+__global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_xy_kernel(const __grid_constant__ RLArgs A) {
   constexpr int R = (K - 1) / 2;
   constexpr int LEAD = (R + CW - 1) / CW * CW;       // x halo in whole chunks
   constexpr int NCH = (CW + 2 * LEAD) / CW;          // chunks of the x window
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(64) rl_xy_edge_kernel(const __grid_constant__ 
 
 // ---- z pass + RL epilogue ---------------------------------------------------------------------------------------
 template <int K, int MODE, int CW>
-__global__ void __launch_bounds__(RLS_NT, 2) rl_z_kernel(const __grid_constant__ RLArgs A) {
+__global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid_constant__ RLArgs A) {
   constexpr int R = (K - 1) / 2;
   const size_t plane = (size_t)A.ny * A.nx;
   const size_t i0 = ((size_t)blockIdx.x * RLS_NT + threadIdx.x) * CW;   // first voxel of the thread inside a plane
