@@ -263,6 +263,44 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+class numa_local:
+    """Context: run on the CPUs of the NUMA node the given GPU hangs off (so freshly allocated host memory is
+    first-touched there), then restore the affinity.  Silently does nothing when the topology cannot be read."""
+
+    def __init__(self, gpu_index):
+        self.gpu, self.saved = gpu_index, None
+
+    def __enter__(self):
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(self.gpu)
+            bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+                node = int(fh.read().strip())
+            if node < 0:
+                return self
+            with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+                cpus = set()
+                for part in fh.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, cpus & allowed)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
 def workload_config(sp):
     return {"workload": "BASELINE.json configs[1]: %d views %dx%dx%d float32, affine resampling + blending-weighted "
                         "additive fusion, fused frame %s at spacing 1" % (NVIEWS, *VIEW_SHAPE, "x".join(str(int(s)) for s in sp["size"])),
@@ -331,10 +369,16 @@ def run_b200(args):
     # Every step copies its own inputs in and its result out; the copies of consecutive steps are pipelined on
     # three streams over two sets of device buffers (PCIe is full duplex: H2D of step i+1 runs under the kernel
     # and the D2H of step i).
-    pinned = [torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for v in views]
+    with numa_local(local):   # first-touch the pinned buffers on the NUMA node of this rank's GPU (matters at N > 1)
+        pinned = [torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for v in views]
+        for p in pinned:
+            p.zero_()
     for p, v in zip(pinned, views):
         p.copy_(v)
-    out_host = [torch.empty(dims, dtype=torch.uint16, pin_memory=True) for _ in range(2)]
+    with numa_local(local):
+        out_host = [torch.empty(dims, dtype=torch.uint16, pin_memory=True) for _ in range(2)]
+        for o in out_host:
+            o.zero_()
     dsets = [[torch.empty_like(v) for v in views] for _ in range(2)]
     outs = [torch.empty(dims, dtype=torch.uint16, device=dev) for _ in range(2)]
     vsets = [fusion.build_viewset(d, props, params, sp, weights="blending") for d in dsets]
