@@ -17,6 +17,7 @@
 // Accumulation order per output is fixed (x taps ascending, y and z contributions in ascending row / plane
 // order), so z-slabs and chunks reproduce the whole volume bit for bit, as in the fused kernel.
 #pragma once
+#include <type_traits>
 
 namespace mvf {
 
@@ -81,24 +82,26 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_xy_kernel(const __gri
   // Row pointers advance by nx inside the volume; only rows that go through the index map (t < 0 or t >= ny, i.e.
   // the ramps at the volume borders) pay for ext_index.
   auto row_ptr = [&](int t) { return src + (size_t)ext_index(t, A.ny, A.ksz_y) * A.nx; };
-  auto load_window = [&](const float* __restrict__ rowp) {
+  auto load_window = [&](const float* __restrict__ rowp) {   // rowp: first column of the thread's window
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       float v[CW];
-      vec_load<CW>(rowp + (xw - LEAD) + j * CW, v);
+      vec_load<CW>(rowp + j * CW, v);
 #pragma unroll
       for (int i = 0; i < CW; ++i) win[j * CW + i] = v[i];
     }
   };
-  const float* __restrict__ cur = row_ptr(yo0 - R);                 // row t
-  const float* __restrict__ far = row_ptr(yo0 - R + RLS_AHEAD);     // row t + RLS_AHEAD (L2 prefetch)
+  // per-thread pointers (source offsets include the thread's columns): row t, row t + RLS_AHEAD, output row t - R
+  const float* __restrict__ cur = row_ptr(yo0 - R) + (xw - LEAD);
+  const float* __restrict__ far = row_ptr(yo0 - R + RLS_AHEAD) + x0;
+  float* __restrict__ optr = dst + (ptrdiff_t)(yo0 - 2 * R) * A.nx + x0;   // first stored at t = yo0 + R
   load_window(cur);
-  for (int t = yo0 - R; t < yo1 + R; ++t) {
-    if (RLS_AHEAD > 0 && t + RLS_AHEAD < yo1 + R) prefetch_l2(far + x0);
-    {
-      const int tf = t + RLS_AHEAD + 1;
-      far = (tf >= 1 && tf < A.ny) ? far + A.nx : row_ptr(tf);
-    }
+  // One step = x pass of row t, request of row t+1, y pass, store of output row t - R.  INTERIOR steps know that the
+  // rows t+1 and t+RLS_AHEAD+1 lie inside the volume: all three pointers just advance by nx (no index map, no
+  // multiplies); the few steps at the chunk / volume borders take the general path.
+  auto step = [&](int t, auto interior_tag) {
+    constexpr bool INTERIOR = decltype(interior_tag)::value;
+    if (RLS_AHEAD > 0 && (INTERIOR || t + RLS_AHEAD < yo1 + R)) prefetch_l2(far);
     float o[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) o[i] = 0.f;
@@ -108,8 +111,15 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_xy_kernel(const __gri
 #pragma unroll
       for (int i = 0; i < CW; ++i) o[i] = fmaf(kj, win[LEAD + i + R - j], o[i]);
     }
-    cur = (t + 1 >= 1 && t + 1 < A.ny) ? cur + A.nx : row_ptr(t + 1);
-    if (t + 1 < yo1 + R) load_window(cur);
+    if (INTERIOR) {
+      cur += A.nx;
+      far += A.nx;
+      load_window(cur);
+    } else {
+      cur = row_ptr(t + 1) + (xw - LEAD);
+      far = row_ptr(t + RLS_AHEAD + 1) + x0;
+      if (t + 1 < yo1 + R) load_window(cur);
+    }
     float e[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -118,9 +128,15 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_xy_kernel(const __gri
       for (int m = 0; m < K - 2; ++m) S[i][m] = fmaf(A.ky[m + 1], o[i], S[i][m + 1]);
       S[i][K - 2] = A.ky[K - 1] * o[i];
     }
-    const int y = t - R;
-    if (y >= yo0) vec_store<CW>(dst + (size_t)y * A.nx + x0, e);
-  }
+    if (INTERIOR || t - R >= yo0) vec_store<CW>(optr, e);
+    optr += A.nx;
+  };
+  // interior steps: the output row exists (t - R >= yo0), rows t+1 and t+RLS_AHEAD+1 are real rows, t+1 is needed
+  const int t_lo = max(yo0 + R, 0), t_hi = min(yo1 + R - 1, A.ny - RLS_AHEAD - 1);
+  int t = yo0 - R;
+  for (; t < min(t_lo, yo1 + R); ++t) step(t, std::false_type{});
+  for (; t < t_hi; ++t) step(t, std::true_type{});
+  for (; t < yo1 + R; ++t) step(t, std::false_type{});
 }
 
 // The 2 * LEAD columns next to the x borders of every row: thread = column, index-mapped scalar window (the K source
