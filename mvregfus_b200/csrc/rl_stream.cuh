@@ -56,7 +56,8 @@ constexpr int RLS_NEAR = MVF_RLS_NEAR;     // rows / planes the L1 prefetch runs
 
 // ---- x and y passes of every plane -------------------------------------------------------------------------
 template <int K, int CW>
-__global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_xy_kernel(const __grid_constant__ RLArgs A) {
+// (43 taps: window + shift register exceed 128 registers, one CTA per SM)
+__global__ void __launch_bounds__(RLS_NT, K > 37 ? 1 : MVF_RLS_MINB) rl_xy_kernel(const __grid_constant__ RLArgs A) {
   constexpr int R = (K - 1) / 2;
   constexpr int LEAD = (R + CW - 1) / CW * CW;       // x halo in whole chunks
   constexpr int NCH = (CW + 2 * LEAD) / CW;          // chunks of the x window
