@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(RLS_NT, K > 37 ? 1 : MVF_RLS_MINB) rl_xy_kerne
       for (int i = 0; i < CW; ++i) win[j * CW + i] = v[i];
     }
   };
-  // per-thread pointers (source offsets include the thread's columns): row t, row t + RLS_AHEAD, output row t - R
+  // per-thread pointers (source offsets include the thread's columns): row t, row t + RLS_AHEAD; output row t - R as an offset
   const float* __restrict__ cur = row_ptr(yo0 - R) + (xw - LEAD);
   const float* __restrict__ far = row_ptr(yo0 - R + RLS_AHEAD) + x0;
-  float* __restrict__ optr = dst + (ptrdiff_t)(yo0 - 2 * R) * A.nx + x0;   // first stored at t = yo0 + R
+  ptrdiff_t ooff = (ptrdiff_t)(yo0 - 2 * R) * A.nx + x0;   // offset of output row t - R in dst; first stored at t = yo0 + R
   load_window(cur);
   // One step = x pass of row t, request of row t+1, y pass, store of output row t - R.  INTERIOR steps know that the
   // rows t+1 and t+RLS_AHEAD+1 lie inside the volume: all three pointers just advance by nx (no index map, no
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(RLS_NT, K > 37 ? 1 : MVF_RLS_MINB) rl_xy_kerne
       for (int m = 0; m < K - 2; ++m) S[i][m] = fmaf(A.ky[m + 1], o[i], S[i][m + 1]);
       S[i][K - 2] = A.ky[K - 1] * o[i];
     }
-    if (INTERIOR || t - R >= yo0) vec_store<CW>(optr, e);
-    optr += A.nx;
+    if (INTERIOR || t - R >= yo0) vec_store<CW>(dst + ooff, e);
+    ooff += A.nx;
   };
   // interior steps: the output row exists (t - R >= yo0), rows t+1 and t+RLS_AHEAD+1 are real rows, t+1 is needed
   const int t_lo = max(yo0 + R, 0), t_hi = min(yo1 + R - 1, A.ny - RLS_AHEAD - 1);
