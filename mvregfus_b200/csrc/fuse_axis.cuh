@@ -1,0 +1,462 @@
+// K2, bandwidth-shaped variant for views whose index map  u_view = matrix' * i_fused + offset'  is a signed axis
+// permutation times a diagonal (the reference's default acquisition geometry: stage rotations of 0/90/180/270 deg,
+// mvregfus/mv_graph.py:66, with per-axis scale): every view coordinate then depends on ONE fused index, so
+// everything the per-voxel arithmetic of resample_fuse.cu derives from float64 coordinates (floor index, lerp
+// weights, scipy's inside test, the ITK sample of the blending field, mv:1486-1496, 1606-1610, 3558-3611) becomes
+// three small per-axis tables per view and tile.  Same results as the general kernel to float32 rounding.
+//
+//   * CTA = 16x8x32 (z,y,x) output tile, 256 threads: warp <-> y row, lane <-> x, a thread walks 16 z voxels.
+//   * The source brick of every view is a dense box fetched by TMA (cp.async.bulk.tensor.3d, one CUtensorMap per
+//     view, out-of-volume elements zero filled by the hardware) into one of two shared-memory buffers; the brick
+//     of view v+2 is requested as soon as view v has been gathered, completion is tracked with mbarriers.  No LSU
+//     instruction, address arithmetic or bounds test is spent on staging.
+//   * Per z step a thread needs the bilinear value of two neighbouring planes of the brick along the view axis its
+//     z walk follows; the plane index is uniform over the tile, so the planes are carried from step to step
+//     (scale ~1: one new plane = 4 LDS + 6 FP per voxel-view; 2x up-sampling: every other step loads nothing).
+//   * Lerps are  (1-t)*a + t*b  with both weights taken from the float64 fraction: no cancellation for the
+//     non-negative data of the path, exact on constant neighbourhoods, zero when the voxel is outside the view
+//     (both weights are 0 there, which is scipy's mode='constant', cval=0).
+//   * Blending weights: per view and tile one of {0, 1, 1-D ramp along z / y / x, general}; tiles on which every
+//     view is 0 or 1 (the interior) skip the per-voxel normalisation altogether.
+#pragma once
+#include <cuda.h>
+
+namespace mvf {
+
+constexpr int AZ = 16, AY = 8, AX = 32, ANT = 256, ATAB = AZ + AY + AX;
+static_assert(AY * AX == ANT, "one thread per (y,x) column of the tile");
+constexpr int AST = 4;   // tiles per super-tile edge (rasterisation order: neighbours in space run close in time)
+
+struct TmaMaps { CUtensorMap m[MVF_MAX_VIEWS]; };
+
+// Everything the kernel needs per view, per FUSED axis a (0 = z, 1 = y, 2 = x); kept small so that the whole
+// parameter block (tensor maps included) stays below 4 KB.
+struct AxView {
+  double sc[3], of[3];     // view coordinate along view axis vax[a]:  u = sc[a] * g_a + of[a]   (matrix'/offset', mv:1494-1496)
+  double wsc[3], wof[3];   // blending-field coordinate along field axis vax[a]                   (mv:3567, 3604)
+  const float* prof;       // 3 x MVF_SIG_N border profiles, field axis order
+  int vax[3];    // vax[a] = view axis driven by fused axis a
+  int n[3];      // n[a] = view extent along view axis vax[a]
+  int box[3];    // brick extents in view axis order (z, y, x): the TMA box
+  int str[3];    // str[a] = element stride, inside the brick, of view axis vax[a]
+  int one_lo[3], one_hi[3];   // plateau of profile vax[a]
+  int bytes;     // box bytes (the mbarrier's expected transaction count)
+  int wmode;
+  int xalign;    // elements per 16 bytes
+};
+struct AxArgs {
+  AxView v[MVF_MAX_VIEWS];
+  void* out;
+  float* outf;
+  int dims[3], org[3];
+  int nviews;
+  int brick_stride;   // bytes between the two brick buffers (multiple of 128)
+};
+
+enum { AW_ZERO = 0, AW_ONE = 1, AW_Z = 2, AW_Y = 3, AW_X = 4, AW_3D = 5 };
+
+struct AxTile {
+  int b0[3];   // view index of brick element (0,0,0); b0[a] belongs to view axis vax[a]
+  int skip;    // the tile sees no voxel of the view (or its weight is 0 everywhere): nothing to gather
+  int wcls;    // AW_*
+};
+struct __align__(16) GTab { int off; float t, omt; int mode; };   // gather table entry of one fused index
+struct __align__(16) WTab { float v0, v1, t, w1; };               // blending-field entry: profile pair, fraction (-1 = outside), 1-D weight
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX) ---------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MVF_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MVF_DONE_%=;\n\t"
+      "bra MVF_WAIT_%=;\n\t"
+      "MVF_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int cx, int cy, int cz) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+      "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(cx), "r"(cy), "r"(cz) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ float tap(const T* p, int off);
+template <> __device__ __forceinline__ float tap<float>(const float* p, int off) { return p[off]; }
+template <> __device__ __forceinline__ float tap<uint16_t>(const uint16_t* p, int off) { return u16_to_float(p[off]); }
+
+// RN(w / s) from rs = RN(1 / s): one product, one exact residual, one correction (Markstein)
+__device__ __forceinline__ float div_by(float w, float s, float rs) {
+  const float q = w * rs;
+  return fmaf(fmaf(-q, s, w), rs, q);
+}
+
+__device__ __forceinline__ bool ax_tile_origin(const int dims[3], int& z0, int& y0, int& x0) {
+  const unsigned snx = (dims[2] + AX * AST - 1) / (AX * AST), sny = (dims[1] + AY * AST - 1) / (AY * AST);
+  const unsigned b = blockIdx.x;
+  const unsigned inner = b & (AST * AST * AST - 1), sup = b / (AST * AST * AST);
+  const unsigned sx = sup % snx, sy = (sup / snx) % sny, sz = sup / (snx * sny);
+  x0 = (int)((sx * AST + (inner & 3)) * AX);
+  y0 = (int)((sy * AST + ((inner >> 2) & 3)) * AY);
+  z0 = (int)((sz * AST + (inner >> 4)) * AZ);
+  return z0 < dims[0] && y0 < dims[1] && x0 < dims[2];
+}
+
+// Per view: where the tile's brick starts, whether it holds anything, and the class of its blending weights.
+__device__ __forceinline__ void ax_make_tile(const AxView& av, const int g0[3], AxTile& t) {
+  const int T[3] = {AZ, AY, AX};
+  bool skip = false, zero = av.wmode == MVF_W_OFF;
+  int active = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double ua = fma(av.sc[a], (double)g0[a], av.of[a]), ub = fma(av.sc[a], (double)(g0[a] + T[a] - 1), av.of[a]);
+    const double lo = fmin(ua, ub), hi = fmax(ua, ub);
+    skip = skip || hi < 0.0 || lo > (double)(av.n[a] - 1);
+    int b = __double2int_rd(fmax(lo, -1.0e9));
+    if (av.vax[a] == 2) b &= ~(av.xalign - 1);     // TMA: the box must start on a 16-byte boundary of the view's rows
+    t.b0[a] = b;                                   // indexed by FUSED axis
+    if (av.wmode != MVF_W_OFF) {   // fused index -> blending-field index is monotone per axis: the end points bound the tile
+      const double ca = fma(av.wsc[a], (double)g0[a], av.wof[a]), cb = fma(av.wsc[a], (double)(g0[a] + T[a] - 1), av.wof[a]);
+      const double clo = fmin(ca, cb), chi = fmax(ca, cb);
+      zero = zero || chi < -0.5 || clo >= (double)MVF_SIG_N - 0.5;
+      const bool plateau = clo >= (double)av.one_lo[a] && chi < (double)av.one_hi[a];
+      active |= plateau ? 0 : (1 << a);
+    }
+  }
+  t.wcls = zero ? AW_ZERO : (active == 0 ? AW_ONE : (active == 1 ? AW_Z : (active == 2 ? AW_Y : (active == 4 ? AW_X : AW_3D))));
+  t.skip = skip || zero;
+}
+
+// table entries of fused index g along fused axis a
+__device__ __forceinline__ void ax_gather_entry(const AxView& av, const AxTile& t, int a, int g, bool first, GTab& e) {
+  const int nb = av.box[av.vax[a]];   // brick extent along the view axis this fused axis drives
+  const double u = fma(av.sc[a], (double)g, av.of[a]);
+  const int j = __double2int_rd(fmin(fmax(u, -1.0e9), 1.0e9));
+  const double fr = u - (double)j;
+  const bool inside = u >= 0.0 && u <= (double)(av.n[a] - 1);   // scipy mode='constant': outside -> 0
+  e.t = inside ? (float)fr : 0.f;
+  e.omt = inside ? (float)(1.0 - fr) : 0.f;
+  const int rel = max(0, min(j - t.b0[a], nb - 2));
+  e.off = rel * av.str[a];
+  int mode = 3;   // z walk: how the plane pair moves relative to the previous step
+  if (!first) {
+    const double up = fma(av.sc[a], (double)(g - 1), av.of[a]);
+    const int jp = __double2int_rd(fmin(fmax(up, -1.0e9), 1.0e9));
+    const int relp = max(0, min(jp - t.b0[a], nb - 2));
+    const int dl = rel - relp;
+    mode = dl == 0 ? 0 : (dl == 1 ? 1 : (dl == -1 ? 2 : 3));
+  }
+  e.mode = mode;
+}
+
+__device__ __forceinline__ void ax_weight_entry(const AxView& av, int a, int g, WTab& e) {
+  const int d = av.vax[a];
+  const double c = fma(av.wsc[a], (double)g, av.wof[a]);
+  const bool inside = c >= -0.5 && c < (double)MVF_SIG_N - 0.5;   // ITK: valid on [-0.5, N-0.5), neighbours clamped
+  int i = __double2int_rd(fmin(fmax(c, -1.0e6), 1.0e6));
+  double fr = c - (double)i;
+  if (i < 0) { i = 0; fr = 0.0; }
+  if (i >= MVF_SIG_N - 1) { i = MVF_SIG_N - 1; fr = 0.0; }
+  const int i1 = min(i + 1, MVF_SIG_N - 1);
+  const float* f = av.prof + d * MVF_SIG_N;
+  e.v0 = __ldg(f + i);
+  e.v1 = __ldg(f + i1);
+  const float tt = (float)fr;
+  e.t = inside ? tt : -1.f;
+  e.w1 = inside ? fmaf(e.v1 - e.v0, tt, e.v0) : 0.f;
+}
+
+// ITK-linear sample of min(f_z, f_y, f_x) from the three per-axis entries (lerp x, then y, then z)
+__device__ __forceinline__ float ax_weight_3d(const WTab& ez, const WTab& ey, const WTab& ex) {
+  const float m00 = fminf(ez.v0, ey.v0), m01 = fminf(ez.v0, ey.v1), m10 = fminf(ez.v1, ey.v0), m11 = fminf(ez.v1, ey.v1);
+  const float v000 = fminf(m00, ex.v0), v001 = fminf(m00, ex.v1), v010 = fminf(m01, ex.v0), v011 = fminf(m01, ex.v1);
+  const float v100 = fminf(m10, ex.v0), v101 = fminf(m10, ex.v1), v110 = fminf(m11, ex.v0), v111 = fminf(m11, ex.v1);
+  const float x00 = fmaf(v001 - v000, ex.t, v000);
+  const float x01 = fmaf(v011 - v010, ex.t, v010);
+  const float x10 = fmaf(v101 - v100, ex.t, v100);
+  const float x11 = fmaf(v111 - v110, ex.t, v110);
+  const float y0 = fmaf(x01 - x00, ey.t, x00);
+  const float y1 = fmaf(x11 - x10, ey.t, x10);
+  const float w = fmaf(y1 - y0, ez.t, y0);
+  return (ez.t >= 0.f && ey.t >= 0.f && ex.t >= 0.f) ? w : 0.f;
+}
+
+#ifndef MVF_AX_MINB
+#define MVF_AX_MINB 2
+#endif
+
+template <typename T, bool WANT_F32>
+__global__ void __launch_bounds__(ANT, MVF_AX_MINB)
+fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxArgs X) {
+  extern __shared__ __align__(128) unsigned char ax_smem[];
+  __shared__ GTab gt[MVF_MAX_VIEWS][ATAB];
+  __shared__ WTab wt[MVF_MAX_VIEWS][ATAB];
+  __shared__ AxTile tv[MVF_MAX_VIEWS];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ int live[MVF_MAX_VIEWS], nlive_s, nweight_s, uniform_s;
+
+  int z0, y0, x0;
+  if (!ax_tile_origin(X.dims, z0, y0, x0)) return;
+  const int tid = threadIdx.x;
+  const int g0[3] = {z0 + X.org[0], y0 + X.org[1], x0 + X.org[2]};
+  unsigned char* const bricks = ax_smem;
+  // TMA coordinates of a view's brick: (x, y, z) of the view, from the per-fused-axis starts
+  auto issue = [&](int v, int b) {
+    const AxView& av = X.v[v];
+    int c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[av.vax[a]] = tv[v].b0[a];
+    mbar_expect_tx(&mbar[b], (unsigned)av.bytes);
+    tma_load_3d(bricks + b * X.brick_stride, &TM.m[v], &mbar[b], c[2], c[1], c[0]);
+  };
+
+  if (tid < X.nviews) ax_make_tile(X.v[tid], g0, tv[tid]);
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0, nw = 0, uni = 1;
+    for (int v = 0; v < X.nviews; ++v) {
+      if (!tv[v].skip) live[n++] = v;
+      if (tv[v].wcls != AW_ZERO) ++nw;
+      if (tv[v].wcls > AW_ONE) uni = 0;
+    }
+    nlive_s = n; nweight_s = nw; uniform_s = uni;
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int b = 0; b < 2 && b < n; ++b) issue(live[b], b);
+  }
+  // per-axis tables of every view that takes part (gather: views with data here; weights: views with a ramp here)
+  for (int e = tid; e < X.nviews * ATAB; e += ANT) {
+    const int v = e / ATAB, i = e - v * ATAB;
+    const int a = i < AZ ? 0 : (i < AZ + AY ? 1 : 2);
+    const int idx = i - (a == 0 ? 0 : (a == 1 ? AZ : AZ + AY));
+    const AxTile& t = tv[v];
+    if (!t.skip) ax_gather_entry(X.v[v], t, a, g0[a] + idx, idx == 0, gt[v][i]);
+    if (t.wcls > AW_ONE) ax_weight_entry(X.v[v], a, g0[a] + idx, wt[v][i]);
+  }
+  __syncthreads();
+
+  const int ty = tid >> 5, tx = tid & 31;
+  const int nlive = nlive_s;
+  const bool uniform = uniform_s != 0;
+  const float wn_uniform = __fdiv_rn(1.f, (float)max(nweight_s, 1));   // every weighted view has w = 1 here
+
+  // ---- pass 1 over the weights (only tiles that touch a ramp): S = sum_v w_v, 0 -> 1 (mv:3627-3631) ---------
+  float S[AZ], rS[AZ];
+  if (!uniform) {
+#pragma unroll
+    for (int k = 0; k < AZ; ++k) S[k] = 0.f;
+    for (int v = 0; v < X.nviews; ++v) {
+      const int cls = tv[v].wcls;
+      if (cls == AW_ZERO) continue;
+      if (cls == AW_Z) {
+#pragma unroll
+        for (int k = 0; k < AZ; ++k) S[k] += wt[v][k].w1;
+      } else if (cls == AW_3D) {
+        const WTab ey = wt[v][AZ + ty], ex = wt[v][AZ + AY + tx];
+#pragma unroll
+        for (int k = 0; k < AZ; ++k) S[k] += ax_weight_3d(wt[v][k], ey, ex);
+      } else {
+        const float w = cls == AW_ONE ? 1.f : (cls == AW_Y ? wt[v][AZ + ty].w1 : wt[v][AZ + AY + tx].w1);
+#pragma unroll
+        for (int k = 0; k < AZ; ++k) S[k] += w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < AZ; ++k) {
+      S[k] = S[k] == 0.f ? 1.f : S[k];
+      rS[k] = __frcp_rn(S[k]);
+    }
+  }
+
+  uint32_t acc[AZ];
+  float accf[AZ];
+#pragma unroll
+  for (int k = 0; k < AZ; ++k) { acc[k] = 0u; accf[k] = 0.f; }
+
+  for (int li = 0; li < nlive; ++li) {
+    const int v = live[li], b = li & 1;
+    const AxView& av = X.v[v];
+    const T* __restrict__ br = reinterpret_cast<const T*>(bricks + b * X.brick_stride);
+    const GTab gy = gt[v][AZ + ty], gx = gt[v][AZ + AY + tx];
+    const int sZ = av.str[0], sY = av.str[1], sX = av.str[2];
+    const T* __restrict__ p = br + gy.off + gx.off;
+    const float tY = gy.t, oY = gy.omt, tX = gx.t, oX = gx.omt;
+    const int cls = tv[v].wcls;
+    WTab ey, ex;
+    float wthread = 1.f;
+    if (!uniform) {
+      if (cls == AW_3D) { ey = wt[v][AZ + ty]; ex = wt[v][AZ + AY + tx]; }
+      else if (cls == AW_Y) wthread = wt[v][AZ + ty].w1;
+      else if (cls == AW_X) wthread = wt[v][AZ + AY + tx].w1;
+    }
+    mbar_wait(&mbar[b], (unsigned)((li >> 1) & 1));
+
+    auto plane = [&](int off) {
+      const float a = tap<T>(p, off), bb = tap<T>(p, off + sX), c = tap<T>(p, off + sY), d = tap<T>(p, off + sY + sX);
+      const float r0 = fmaf(tX, bb, oX * a), r1 = fmaf(tX, d, oX * c);
+      return fmaf(tY, r1, oY * r0);
+    };
+    float P0 = 0.f, P1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < AZ; ++k) {
+      const GTab gz = gt[v][k];   // uniform over the CTA: one broadcast LDS.128
+      if (gz.mode == 3) { P0 = plane(gz.off); P1 = plane(gz.off + sZ); }
+      else if (gz.mode == 1) { P0 = P1; P1 = plane(gz.off + sZ); }
+      else if (gz.mode == 2) { P1 = P0; P0 = plane(gz.off); }
+      float vv = fmaf(gz.t, P1, gz.omt * P0);
+      float wn;
+      if (uniform) {
+        wn = wn_uniform;
+      } else {
+        float w = wthread;
+        if (cls == AW_Z) w = wt[v][k].w1;
+        else if (cls == AW_3D) w = ax_weight_3d(wt[v][k], ey, ex);
+        wn = div_by(w, S[k], rS[k]);
+      }
+      if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));
+      acc[k] += trunc_product_u16(wn, vv);
+      if (WANT_F32) accf[k] = fmaf(wn, vv, accf[k]);
+    }
+    __syncthreads();   // every thread is done with this brick buffer
+    if (tid == 0 && li + 2 < nlive) issue(live[li + 2], b);
+  }
+
+  const int y = y0 + ty, x = x0 + tx;
+  if (y >= X.dims[1] || x >= X.dims[2]) return;
+  uint16_t* out = reinterpret_cast<uint16_t*>(X.out);
+#pragma unroll
+  for (int k = 0; k < AZ; ++k) {
+    const int z = z0 + k;
+    if (z >= X.dims[0]) break;
+    const size_t idx = ((size_t)z * X.dims[1] + y) * X.dims[2] + x;
+    out[idx] = (uint16_t)(sizeof(T) == 2 ? (acc[k] & 0xFFFFu) : min(acc[k], 65535u));
+    if (WANT_F32) X.outf[idx] = accf[k];
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tensor_map_encode_fn tensor_map_encoder() {
+  static tensor_map_encode_fn fn = []() -> tensor_map_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<tensor_map_encode_fn>(p);
+  }();
+  return fn;
+}
+
+// Is view `h` (index map matrix/offset, blending map wmatrix/woffset) a signed permutation times a diagonal on the
+// box [org, org+dims)?  Off-axis terms that move a coordinate by less than 1e-9 voxels over the box (cos(pi/2) =
+// 6e-17 of a float64 rotation matrix) count as zero.  Fills vax/box/str/bytes.
+static bool axis_view(const mvf_view& h, const int32_t dims[3], const int32_t org[3], AxView& av) {
+  const int es = h.dtype == MVF_U16 ? 2 : 4, vec = 16 / es;
+  if ((reinterpret_cast<uintptr_t>(h.data) & 15u) || (h.dims[2] % vec) != 0) return false;   // TMA: 16-byte base and strides
+  const int T[3] = {AZ, AY, AX};
+  int used = 0;
+  for (int d = 0; d < 3; ++d) {
+    int a = 0;
+    for (int l = 1; l < 3; ++l)
+      if (fabs(h.matrix[d * 3 + l]) > fabs(h.matrix[d * 3 + a])) a = l;
+    if (used & (1 << a)) return false;
+    used |= 1 << a;
+    for (int l = 0; l < 3; ++l) {
+      if (l == a) continue;
+      const double reach = (double)(fabs((double)org[l]) + dims[l] + T[l]);
+      if (fabs(h.matrix[d * 3 + l]) * reach > 1e-9) return false;
+      if (h.weight_mode != MVF_W_OFF && fabs(h.wmatrix[d * 3 + l]) * reach > 1e-9) return false;
+    }
+    const double sc = fabs(h.matrix[d * 3 + a]);
+    if (!(sc > 0.0) || !(sc < 64.0)) return false;
+    av.vax[a] = d;
+    av.box[d] = (int)floor(sc * (T[a] - 1)) + 3;
+    av.sc[a] = h.matrix[d * 3 + a];
+    av.of[a] = h.offset[d];
+    av.wsc[a] = h.wmatrix[d * 3 + a];
+    av.wof[a] = h.woffset[d];
+    av.n[a] = h.dims[d];
+    av.one_lo[a] = h.one_lo[d];
+    av.one_hi[a] = h.one_hi[d];
+  }
+  av.prof = h.profiles;
+  av.wmode = h.weight_mode;
+  // dense boxes: rows of whole 16-byte chunks; (chunks per row) and (rows per plane) odd, so that a warp walking
+  // along view y or z meets 8 different bank groups instead of 1 or 2
+  av.xalign = vec;
+  av.box[2] = (av.box[2] + (vec - 1) + vec - 1) / vec;   // + (vec - 1): the box start is aligned down to 16 bytes
+  av.box[2] = (av.box[2] | 1) * vec;
+  av.box[1] |= 1;
+  if (av.box[0] > 256 || av.box[1] > 256 || av.box[2] > 256) return false;
+  const int str_of[3] = {av.box[1] * av.box[2], av.box[2], 1};
+  for (int a = 0; a < 3; ++a) av.str[a] = str_of[av.vax[a]];
+  av.bytes = av.box[0] * av.box[1] * av.box[2] * es;
+  return av.bytes <= 48 * 1024;
+}
+
+static int encode_view_map(const mvf_view& h, const AxView& av, CUtensorMap* map) {
+  tensor_map_encode_fn enc = tensor_map_encoder();
+  if (!enc) return fail(MVF_ERR_CUDA, "%s%s", "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t es = h.dtype == MVF_U16 ? 2 : 4;
+  const cuuint64_t gdim[3] = {(cuuint64_t)h.dims[2], (cuuint64_t)h.dims[1], (cuuint64_t)h.dims[0]};
+  const cuuint64_t gstr[2] = {(cuuint64_t)h.dims[2] * es, (cuuint64_t)h.dims[2] * h.dims[1] * es};
+  const cuuint32_t box[3] = {(cuuint32_t)av.box[2], (cuuint32_t)av.box[1], (cuuint32_t)av.box[0]};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, h.dtype == MVF_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(h.data), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MVF_ERR_CUDA, "%s%s", "cuTensorMapEncodeTiled failed");
+  return MVF_OK;
+}
+
+static dim3 ax_tile_grid(const int32_t dims[3]) {
+  unsigned nx = (dims[2] + AX * AST - 1) / (AX * AST), ny = (dims[1] + AY * AST - 1) / (AY * AST), nz = (dims[0] + AZ * AST - 1) / (AZ * AST);
+  return dim3(nx * ny * nz * AST * AST * AST);
+}
+
+// Launches the axis-aligned kernel when every view qualifies; *taken = 0 (and nothing launched) otherwise.
+static int try_fuse_axis(int nviews, const mvf_view* hv, const KArgs& A, cudaStream_t st, int* taken) {
+  *taken = 0;
+  const char* sel = getenv("MVF_FUSE_KERNEL");   // "general": always the per-voxel kernel (A/B runs, tests)
+  if (sel && !strcmp(sel, "general")) return MVF_OK;
+  AxArgs X;
+  memset(&X, 0, sizeof(X));
+  static_assert(sizeof(AxArgs) + sizeof(TmaMaps) <= 4096, "kernel parameters (tensor maps included) must stay below 4 KB");
+  X.out = A.out; X.outf = A.outf; X.nviews = nviews;
+  for (int d = 0; d < 3; ++d) { X.dims[d] = A.dims[d]; X.org[d] = A.org[d]; }
+  int maxb = 0;
+  for (int v = 0; v < nviews; ++v) {
+    if (hv[v].weight_mode == MVF_W_BLEND_DCT) return MVF_OK;
+    if (!axis_view(hv[v], A.dims, A.org, X.v[v])) return MVF_OK;
+    maxb = X.v[v].bytes > maxb ? X.v[v].bytes : maxb;
+  }
+  X.brick_stride = (maxb + 127) & ~127;
+  TmaMaps TM;
+  for (int v = 0; v < nviews; ++v) {
+    int rc = encode_view_map(hv[v], X.v[v], &TM.m[v]);
+    if (rc) return rc;
+  }
+  const size_t smem = 2 * (size_t)X.brick_stride;
+  auto launch = [&](auto kern) -> int {
+    MVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ax_tile_grid(A.dims), ANT, smem, st>>>(TM, X);
+    MVF_LAUNCHED();
+    return MVF_OK;
+  };
+  *taken = 1;
+  const bool f32 = A.outf != nullptr;
+  if (hv[0].dtype == MVF_U16) return f32 ? launch(fuse_axis_kernel<uint16_t, true>) : launch(fuse_axis_kernel<uint16_t, false>);
+  return f32 ? launch(fuse_axis_kernel<float, true>) : launch(fuse_axis_kernel<float, false>);
+}
+
+}  // namespace mvf

@@ -928,6 +928,9 @@ static int launch_tiles(K kern, const KArgs& A, size_t smem, cudaStream_t st) {
 
 }  // namespace mvf
 
+#include <stdlib.h>
+#include "fuse_axis.cuh"
+
 using namespace mvf;
 
 extern "C" int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* out, float* out_f32,
@@ -941,6 +944,10 @@ extern "C" int mvf_fuse_blend(int nviews, const mvf_view* host_views, uint16_t* 
   if (rc) return rc;
   const size_t smem = brick + (size_t)nviews * TILE_VOX * sizeof(float);
   cudaStream_t st = as_stream(stream);
+  // axis-aligned views (signed permutation x diagonal index maps): TMA-staged, table-driven kernel
+  int taken = 0;
+  rc = try_fuse_axis(nviews, host_views, A, st, &taken);
+  if (rc || taken) return rc;
   if (host_views[0].dtype == MVF_U16)
     return out_f32 ? launch_tiles(fuse_blend_kernel<uint16_t, true>, A, smem, st) : launch_tiles(fuse_blend_kernel<uint16_t, false>, A, smem, st);
   return out_f32 ? launch_tiles(fuse_blend_kernel<float, true>, A, smem, st) : launch_tiles(fuse_blend_kernel<float, false>, A, smem, st);
