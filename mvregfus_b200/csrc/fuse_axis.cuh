@@ -28,6 +28,8 @@ static_assert(AY * AX == ANT, "one thread per (y,x) column of the tile");
 constexpr int AST = 4;   // tiles per super-tile edge (rasterisation order: neighbours in space run close in time)
 
 struct TmaMaps { CUtensorMap m[MVF_MAX_VIEWS]; };
+struct __align__(16) GTab { int off; float t, omt; int mode; };   // gather table entry of one fused index
+struct __align__(16) WTab { float v0, v1, t, w1; };               // blending-field entry: profile pair, fraction (-1 = outside), 1-D weight
 
 // Everything the kernel needs per view, per FUSED axis a (0 = z, 1 = y, 2 = x); kept small so that the whole
 // parameter block (tensor maps included) stays below 4 KB.
@@ -43,6 +45,7 @@ struct AxView {
   int bytes;     // box bytes (the mbarrier's expected transaction count)
   int wmode;
   int xalign;    // elements per 16 bytes
+  int dsz;       // signed stride of one step of the z walk: str[0] * sign(sc[0])
 };
 struct AxArgs {
   AxView v[MVF_MAX_VIEWS];
@@ -51,6 +54,8 @@ struct AxArgs {
   int dims[3], org[3];
   int nviews;
   int brick_stride;   // bytes between the two brick buffers (multiple of 128)
+  GTab* gtab;         // per-axis tables of the box, view-major then z | y | x (ax_tables_kernel)
+  WTab* wtab;
 };
 
 enum { AW_ZERO = 0, AW_ONE = 1, AW_Z = 2, AW_Y = 3, AW_X = 4, AW_3D = 5 };
@@ -59,14 +64,17 @@ struct AxTile {
   int b0[3];   // view index of brick element (0,0,0); b0[a] belongs to view axis vax[a]
   int skip;    // the tile sees no voxel of the view (or its weight is 0 everywhere): nothing to gather
   int wcls;    // AW_*
+  int corr;    // element offset of brick element (0,0,0) in the absolute offsets of the tables
+  int regular; // the z walk never jumps over a plane inside this tile
 };
-struct __align__(16) GTab { int off; float t, omt; int mode; };   // gather table entry of one fused index
-struct __align__(16) WTab { float v0, v1, t, w1; };               // blending-field entry: profile pair, fraction (-1 = outside), 1-D weight
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX) ---------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -107,68 +115,104 @@ __device__ __forceinline__ bool ax_tile_origin(const int dims[3], int& z0, int& 
   return z0 < dims[0] && y0 < dims[1] && x0 < dims[2];
 }
 
-// Per view: where the tile's brick starts, whether it holds anything, and the class of its blending weights.
-__device__ __forceinline__ void ax_make_tile(const AxView& av, const int g0[3], AxTile& t) {
-  const int T[3] = {AZ, AY, AX};
+// ---- per-axis tables of the whole box, filled once per launch -----------------------------------------------
+// For every view, fused axis a and index i of the box one 16-byte gather entry and one 16-byte blending-field entry:
+// all float64 coordinate work of a launch happens here ((nz + ny + nx) * V threads); the tiles of the main kernel
+// only copy their slices.
+//   gather entry, y/x axes: j = floor(u), t / omt = weights of elements j+1 / j (both 0 when u is outside [0, n-1]:
+//     scipy mode='constant', cval=0).  z axis (the walk): kept in walk direction - j = LEADING plane (the one a step
+//     newly needs: j+1 when the view index grows with z, j when it falls), t = its weight, omt = weight of the trailing
+//     plane; flags bits 0-1: 0 = same plane pair as index i-1, 1 = moved on by one plane, 3 = anything else.
+//   flags bit 2 / 3: u below 0 / above n-1;  bits 8-15: blending-field floor index;  bit 16 / 17: field coordinate
+//     below -0.5 / at or above N-0.5 (ITK: outside).
+__global__ void __launch_bounds__(256) ax_tables_kernel(const __grid_constant__ AxArgs X) {
+  const int ntot = X.dims[0] + X.dims[1] + X.dims[2];
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= X.nviews * ntot) return;
+  const int v = e / ntot, r = e - v * ntot;
+  const int a = r < X.dims[0] ? 0 : (r < X.dims[0] + X.dims[1] ? 1 : 2);
+  const int i = r - (a == 0 ? 0 : (a == 1 ? X.dims[0] : X.dims[0] + X.dims[1]));
+  const AxView& av = X.v[v];
+  const int g = X.org[a] + i;
+  auto floor_of = [&](int gg, double& u) {
+    u = fma(av.sc[a], (double)gg, av.of[a]);
+    return __double2int_rd(fmin(fmax(u, -1.0e9), 1.0e9));
+  };
+  double u;
+  const int j = floor_of(g, u);
+  const double fr = u - (double)j;
+  const bool below = u < 0.0, above = u > (double)(av.n[a] - 1);
+  const float t = (below || above) ? 0.f : (float)fr, omt = (below || above) ? 0.f : (float)(1.0 - fr);
+  GTab ge;
+  int flags = (below ? 4 : 0) | (above ? 8 : 0);
+  if (a != 0) {
+    ge.off = j; ge.t = t; ge.omt = omt;
+  } else {
+    const bool fwd = av.sc[0] > 0.0;
+    ge.off = fwd ? j + 1 : j;
+    ge.t = fwd ? t : omt;
+    ge.omt = fwd ? omt : t;
+    if (i > 0) {
+      double up;
+      const int dl = (j - floor_of(g - 1, up)) * (fwd ? 1 : -1);
+      flags |= dl == 0 ? 0 : (dl == 1 ? 1 : 3);
+    }
+  }
+  ge.off *= av.str[a];   // element offset inside the view's brick layout (the tile subtracts its brick start)
+  WTab we = {1.f, 1.f, 0.f, 1.f};
+  if (av.wmode != MVF_W_OFF) {
+    const int d = av.vax[a];
+    const double c = fma(av.wsc[a], (double)g, av.wof[a]);
+    const bool fbelow = c < -0.5, fabove = !(c < (double)MVF_SIG_N - 0.5);   // ITK: valid on [-0.5, N-0.5), neighbours clamped
+    int k = __double2int_rd(fmin(fmax(c, -1.0e6), 1.0e6));
+    double cf = c - (double)k;
+    if (k < 0) { k = 0; cf = 0.0; }
+    if (k >= MVF_SIG_N - 1) { k = MVF_SIG_N - 1; cf = 0.0; }
+    const int k1 = min(k + 1, MVF_SIG_N - 1);
+    const float* f = av.prof + d * MVF_SIG_N;
+    we.v0 = __ldg(f + k);
+    we.v1 = __ldg(f + k1);
+    const float tt = (float)cf;
+    const bool inside = !fbelow && !fabove;
+    we.t = inside ? tt : -1.f;
+    we.w1 = inside ? fmaf(we.v1 - we.v0, tt, we.v0) : 0.f;
+    flags |= (k << 8) | (fbelow ? 1 << 16 : 0) | (fabove ? 1 << 17 : 0);
+  }
+  ge.mode = flags;
+  X.gtab[e] = ge;
+  X.wtab[e] = we;
+}
+
+// Per view and tile, from the table entries at the two ends of the tile along every axis (index maps are monotone):
+// where the brick starts, whether the tile sees the view at all, the class of its blending weights.
+__device__ __forceinline__ void ax_make_tile(const AxArgs& X, int v, const int loc0[3], AxTile& t) {
+  const AxView& av = X.v[v];
+  const int EXT[3] = {AZ, AY, AX};
+  const int ntot = X.dims[0] + X.dims[1] + X.dims[2];
   bool skip = false, zero = av.wmode == MVF_W_OFF;
-  int active = 0;
+  int active = 0, corr = 0, pre = 0;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const double ua = fma(av.sc[a], (double)g0[a], av.of[a]), ub = fma(av.sc[a], (double)(g0[a] + T[a] - 1), av.of[a]);
-    const double lo = fmin(ua, ub), hi = fmax(ua, ub);
-    skip = skip || hi < 0.0 || lo > (double)(av.n[a] - 1);
-    int b = __double2int_rd(fmax(lo, -1.0e9));
-    if (av.vax[a] == 2) b &= ~(av.xalign - 1);     // TMA: the box must start on a 16-byte boundary of the view's rows
-    t.b0[a] = b;                                   // indexed by FUSED axis
-    if (av.wmode != MVF_W_OFF) {   // fused index -> blending-field index is monotone per axis: the end points bound the tile
-      const double ca = fma(av.wsc[a], (double)g0[a], av.wof[a]), cb = fma(av.wsc[a], (double)(g0[a] + T[a] - 1), av.wof[a]);
-      const double clo = fmin(ca, cb), chi = fmax(ca, cb);
-      zero = zero || chi < -0.5 || clo >= (double)MVF_SIG_N - 0.5;
-      const bool plateau = clo >= (double)av.one_lo[a] && chi < (double)av.one_hi[a];
+    const GTab* g = X.gtab + (size_t)v * ntot + pre;
+    const GTab ea = g[loc0[a]], eb = g[min(loc0[a] + EXT[a] - 1, X.dims[a] - 1)];
+    pre += X.dims[a];
+    const int lead = (a == 0 && av.dsz > 0) ? av.str[0] : 0;   // z entries hold the leading plane
+    int b = min(ea.off - lead, eb.off - lead);                  // element offset of the lowest floor index of the tile
+    if (av.vax[a] == 2) b &= ~(av.xalign - 1);                  // TMA: the box starts on a 16-byte boundary of the view's rows
+    t.b0[a] = b / av.str[a];                                    // exact: offsets are multiples of the stride
+    corr += b;
+    skip = skip || ((ea.mode & eb.mode & 4) != 0) || ((ea.mode & eb.mode & 8) != 0);
+    if (av.wmode != MVF_W_OFF) {
+      zero = zero || ((ea.mode & eb.mode & (1 << 16)) != 0) || ((ea.mode & eb.mode & (1 << 17)) != 0);
+      const int ia = (ea.mode >> 8) & 255, ib = (eb.mode >> 8) & 255;
+      const bool inside = ((ea.mode | eb.mode) & (3 << 16)) == 0;
+      const bool plateau = inside && min(ia, ib) >= av.one_lo[a] && max(ia, ib) < av.one_hi[a];
       active |= plateau ? 0 : (1 << a);
     }
   }
+  t.corr = corr;
   t.wcls = zero ? AW_ZERO : (active == 0 ? AW_ONE : (active == 1 ? AW_Z : (active == 2 ? AW_Y : (active == 4 ? AW_X : AW_3D))));
   t.skip = skip || zero;
-}
-
-// table entries of fused index g along fused axis a
-__device__ __forceinline__ void ax_gather_entry(const AxView& av, const AxTile& t, int a, int g, bool first, GTab& e) {
-  const int nb = av.box[av.vax[a]];   // brick extent along the view axis this fused axis drives
-  const double u = fma(av.sc[a], (double)g, av.of[a]);
-  const int j = __double2int_rd(fmin(fmax(u, -1.0e9), 1.0e9));
-  const double fr = u - (double)j;
-  const bool inside = u >= 0.0 && u <= (double)(av.n[a] - 1);   // scipy mode='constant': outside -> 0
-  e.t = inside ? (float)fr : 0.f;
-  e.omt = inside ? (float)(1.0 - fr) : 0.f;
-  const int rel = max(0, min(j - t.b0[a], nb - 2));
-  e.off = rel * av.str[a];
-  int mode = 3;   // z walk: how the plane pair moves relative to the previous step
-  if (!first) {
-    const double up = fma(av.sc[a], (double)(g - 1), av.of[a]);
-    const int jp = __double2int_rd(fmin(fmax(up, -1.0e9), 1.0e9));
-    const int relp = max(0, min(jp - t.b0[a], nb - 2));
-    const int dl = rel - relp;
-    mode = dl == 0 ? 0 : (dl == 1 ? 1 : (dl == -1 ? 2 : 3));
-  }
-  e.mode = mode;
-}
-
-__device__ __forceinline__ void ax_weight_entry(const AxView& av, int a, int g, WTab& e) {
-  const int d = av.vax[a];
-  const double c = fma(av.wsc[a], (double)g, av.wof[a]);
-  const bool inside = c >= -0.5 && c < (double)MVF_SIG_N - 0.5;   // ITK: valid on [-0.5, N-0.5), neighbours clamped
-  int i = __double2int_rd(fmin(fmax(c, -1.0e6), 1.0e6));
-  double fr = c - (double)i;
-  if (i < 0) { i = 0; fr = 0.0; }
-  if (i >= MVF_SIG_N - 1) { i = MVF_SIG_N - 1; fr = 0.0; }
-  const int i1 = min(i + 1, MVF_SIG_N - 1);
-  const float* f = av.prof + d * MVF_SIG_N;
-  e.v0 = __ldg(f + i);
-  e.v1 = __ldg(f + i1);
-  const float tt = (float)fr;
-  e.t = inside ? tt : -1.f;
-  e.w1 = inside ? fmaf(e.v1 - e.v0, tt, e.v0) : 0.f;
 }
 
 // ITK-linear sample of min(f_z, f_y, f_x) from the three per-axis entries (lerp x, then y, then z)
@@ -186,6 +230,40 @@ __device__ __forceinline__ float ax_weight_3d(const WTab& ez, const WTab& ey, co
   return (ez.t >= 0.f && ey.t >= 0.f && ex.t >= 0.f) ? w : 0.f;
 }
 
+enum { WC_NORMALISED = 0, WC_THREAD = 1, WC_ZTABLE = 2, WC_FIELD = 3 };
+
+// One view's contribution to the thread's AZ voxels.  WC selects where the blending weight comes from (one uniform
+// branch per view instead of one per voxel); REGULAR walks are straight-line code (the new plane is always loaded,
+// the plane pair moves by predicated selects), so the loads of step k+1 overlap the arithmetic of step k.
+template <typename T, int WC, bool REGULAR, bool WANT_F32, typename Plane>
+__device__ __forceinline__ void ax_view_pass(const GTab* __restrict__ gz_tab, const WTab* __restrict__ wz_tab, Plane plane, int dsz,
+                                             float wconst, const WTab& ey, const WTab& ex, const float (&S)[AZ],
+                                             const float (&rS)[AZ], uint32_t (&acc)[AZ], float (&accf)[AZ]) {
+  float Pl = 0.f, Pd = plane(gz_tab[0].off - dsz);   // trailing plane of the first step
+#pragma unroll
+  for (int k = 0; k < AZ; ++k) {
+    const GTab gz = gz_tab[k];   // uniform over the CTA: one broadcast LDS.128
+    if (REGULAR) {
+      const float np = plane(gz.off);
+      const bool adv = gz.mode != 0;
+      Pl = adv ? Pd : Pl;
+      Pd = adv ? np : Pd;
+    } else {
+      if (gz.mode == 3) { Pl = plane(gz.off - dsz); Pd = plane(gz.off); }
+      else if (gz.mode == 1) { Pl = Pd; Pd = plane(gz.off); }
+    }
+    float vv = fmaf(gz.t, Pd, gz.omt * Pl);
+    float wn;
+    if (WC == WC_NORMALISED) wn = wconst;
+    else if (WC == WC_THREAD) wn = div_by(wconst, S[k], rS[k]);
+    else if (WC == WC_ZTABLE) wn = div_by(wz_tab[k].w1, S[k], rS[k]);
+    else wn = div_by(ax_weight_3d(wz_tab[k], ey, ex), S[k], rS[k]);
+    if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));
+    acc[k] += trunc_product_u16(wn, vv);
+    if (WANT_F32) accf[k] = fmaf(wn, vv, accf[k]);
+  }
+}
+
 #ifndef MVF_AX_MINB
 #define MVF_AX_MINB 2
 #endif
@@ -197,48 +275,73 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
   __shared__ GTab gt[MVF_MAX_VIEWS][ATAB];
   __shared__ WTab wt[MVF_MAX_VIEWS][ATAB];
   __shared__ AxTile tv[MVF_MAX_VIEWS];
-  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t mbar[2];    // "brick b has landed" (TMA transaction count)
+  __shared__ __align__(8) uint64_t mfree[2];   // "every warp is done reading brick b" (one arrival per warp)
   __shared__ int live[MVF_MAX_VIEWS], nlive_s, nweight_s, uniform_s;
 
   int z0, y0, x0;
   if (!ax_tile_origin(X.dims, z0, y0, x0)) return;
   const int tid = threadIdx.x;
-  const int g0[3] = {z0 + X.org[0], y0 + X.org[1], x0 + X.org[2]};
-  unsigned char* const bricks = ax_smem;
+  // TMA destinations must be 128-byte aligned whatever the static shared memory adds up to
+  unsigned char* const bricks = ax_smem + ((128u - (smem_u32(ax_smem) & 127u)) & 127u);
   // TMA coordinates of a view's brick: (x, y, z) of the view, from the per-fused-axis starts
   auto issue = [&](int v, int b) {
     const AxView& av = X.v[v];
     int c[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) c[av.vax[a]] = tv[v].b0[a];
+    for (int a = 0; a < 3; ++a) c[av.vax[a]] = tv[v].b0[a];   // view (z, y, x) start of the brick
     mbar_expect_tx(&mbar[b], (unsigned)av.bytes);
     tma_load_3d(bricks + b * X.brick_stride, &TM.m[v], &mbar[b], c[2], c[1], c[0]);
   };
 
-  if (tid < X.nviews) ax_make_tile(X.v[tid], g0, tv[tid]);
-  __syncthreads();
-  if (tid == 0) {
-    int n = 0, nw = 0, uni = 1;
-    for (int v = 0; v < X.nviews; ++v) {
-      if (!tv[v].skip) live[n++] = v;
-      if (tv[v].wcls != AW_ZERO) ++nw;
-      if (tv[v].wcls > AW_ONE) uni = 0;
+  // Warp 7: tile geometry of every view, then the first two brick requests go out at once.  Warps 0-6 meanwhile copy
+  // the tile's slices of the per-axis tables into shared memory (integer work only).
+  const int loc0[3] = {z0, y0, x0};
+  if (tid >= ANT - 32) {
+    const int lane = tid - (ANT - 32);
+    if (lane < X.nviews) ax_make_tile(X, lane, loc0, tv[lane]);
+    {  // does the z walk of a view jump over a plane inside this tile?  (lane k looks at step k)
+      const int ntot = X.dims[0] + X.dims[1] + X.dims[2];
+      const int li = z0 + lane;
+      for (int v = 0; v < X.nviews; ++v) {
+        bool jump = false;
+        if (lane > 0 && lane < AZ && li < X.dims[0]) jump = (X.gtab[(size_t)v * ntot + li].mode & 3) == 3;
+        const unsigned any = __ballot_sync(0xffffffffu, jump);
+        if (lane == 0) tv[v].regular = any == 0u;
+      }
     }
-    nlive_s = n; nweight_s = nw; uniform_s = uni;
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int b = 0; b < 2 && b < n; ++b) issue(live[b], b);
-  }
-  // per-axis tables of every view that takes part (gather: views with data here; weights: views with a ramp here)
-  for (int e = tid; e < X.nviews * ATAB; e += ANT) {
-    const int v = e / ATAB, i = e - v * ATAB;
-    const int a = i < AZ ? 0 : (i < AZ + AY ? 1 : 2);
-    const int idx = i - (a == 0 ? 0 : (a == 1 ? AZ : AZ + AY));
-    const AxTile& t = tv[v];
-    if (!t.skip) ax_gather_entry(X.v[v], t, a, g0[a] + idx, idx == 0, gt[v][i]);
-    if (t.wcls > AW_ONE) ax_weight_entry(X.v[v], a, g0[a] + idx, wt[v][i]);
+    __syncwarp();
+    if (lane == 0) {
+      int n = 0, nw = 0, uni = 1;
+      for (int v = 0; v < X.nviews; ++v) {
+        if (!tv[v].skip) live[n++] = v;
+        if (tv[v].wcls != AW_ZERO) ++nw;
+        if (tv[v].wcls > AW_ONE) uni = 0;
+      }
+      nlive_s = n; nweight_s = nw; uniform_s = uni;
+      mbar_init(&mbar[0], 1);
+      mbar_init(&mbar[1], 1);
+      mbar_init(&mfree[0], ANT / 32);
+      mbar_init(&mfree[1], ANT / 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int b = 0; b < 2 && b < n; ++b) issue(live[b], b);
+    }
+  } else {
+    const int ntot = X.dims[0] + X.dims[1] + X.dims[2];
+    for (int e = tid; e < X.nviews * ATAB; e += ANT - 32) {
+      const int v = e / ATAB, i = e - v * ATAB;
+      const int a = i < AZ ? 0 : (i < AZ + AY ? 1 : 2);
+      const int idx = i - (a == 0 ? 0 : (a == 1 ? AZ : AZ + AY));
+      const int li = loc0[a] + idx, lc = min(li, X.dims[a] - 1);
+      const size_t src = (size_t)v * ntot + (a == 0 ? 0 : (a == 1 ? X.dims[0] : X.dims[0] + X.dims[1])) + lc;
+      GTab ge = X.gtab[src];
+      if (a == 0) {
+        ge.mode = idx == 0 ? 1 : (li > lc ? 0 : (ge.mode & 3));   // the first step finds its trailing plane in the prologue
+      }
+      gt[v][i] = ge;
+      if (X.v[v].wmode != MVF_W_OFF) wt[v][i] = X.wtab[src];
+    }
   }
   __syncthreads();
 
@@ -249,9 +352,9 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
 
   // ---- pass 1 over the weights (only tiles that touch a ramp): S = sum_v w_v, 0 -> 1 (mv:3627-3631) ---------
   float S[AZ], rS[AZ];
-  if (!uniform) {
 #pragma unroll
-    for (int k = 0; k < AZ; ++k) S[k] = 0.f;
+  for (int k = 0; k < AZ; ++k) { S[k] = 0.f; rS[k] = 0.f; }
+  if (!uniform) {
     for (int v = 0; v < X.nviews; ++v) {
       const int cls = tv[v].wcls;
       if (cls == AW_ZERO) continue;
@@ -285,59 +388,58 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
     const AxView& av = X.v[v];
     const T* __restrict__ br = reinterpret_cast<const T*>(bricks + b * X.brick_stride);
     const GTab gy = gt[v][AZ + ty], gx = gt[v][AZ + AY + tx];
-    const int sZ = av.str[0], sY = av.str[1], sX = av.str[2];
-    const T* __restrict__ p = br + gy.off + gx.off;
+    const int sY = av.str[1], sX = av.str[2];
+    const T* __restrict__ p00 = br + (gy.off + gx.off - tv[v].corr);   // table offsets are absolute: subtract the brick start
+    const T* __restrict__ p01 = p00 + sX;
+    const T* __restrict__ p10 = p00 + sY;
+    const T* __restrict__ p11 = p10 + sX;
     const float tY = gy.t, oY = gy.omt, tX = gx.t, oX = gx.omt;
     const int cls = tv[v].wcls;
-    WTab ey, ex;
-    float wthread = 1.f;
-    if (!uniform) {
-      if (cls == AW_3D) { ey = wt[v][AZ + ty]; ex = wt[v][AZ + AY + tx]; }
-      else if (cls == AW_Y) wthread = wt[v][AZ + ty].w1;
-      else if (cls == AW_X) wthread = wt[v][AZ + AY + tx].w1;
-    }
-    mbar_wait(&mbar[b], (unsigned)((li >> 1) & 1));
-
+    const bool regular = tv[v].regular != 0;
+    const int dsz = av.dsz;
+    const WTab ey = wt[v][AZ + ty], ex = wt[v][AZ + AY + tx];
+    const float wthread = cls == AW_Y ? ey.w1 : (cls == AW_X ? ex.w1 : 1.f);
     auto plane = [&](int off) {
-      const float a = tap<T>(p, off), bb = tap<T>(p, off + sX), c = tap<T>(p, off + sY), d = tap<T>(p, off + sY + sX);
+      const float a = tap<T>(p00, off), bb = tap<T>(p01, off), c = tap<T>(p10, off), d = tap<T>(p11, off);
       const float r0 = fmaf(tX, bb, oX * a), r1 = fmaf(tX, d, oX * c);
       return fmaf(tY, r1, oY * r0);
     };
-    float P0 = 0.f, P1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < AZ; ++k) {
-      const GTab gz = gt[v][k];   // uniform over the CTA: one broadcast LDS.128
-      if (gz.mode == 3) { P0 = plane(gz.off); P1 = plane(gz.off + sZ); }
-      else if (gz.mode == 1) { P0 = P1; P1 = plane(gz.off + sZ); }
-      else if (gz.mode == 2) { P1 = P0; P0 = plane(gz.off); }
-      float vv = fmaf(gz.t, P1, gz.omt * P0);
-      float wn;
-      if (uniform) {
-        wn = wn_uniform;
-      } else {
-        float w = wthread;
-        if (cls == AW_Z) w = wt[v][k].w1;
-        else if (cls == AW_3D) w = ax_weight_3d(wt[v][k], ey, ex);
-        wn = div_by(w, S[k], rS[k]);
-      }
-      if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));
-      acc[k] += trunc_product_u16(wn, vv);
-      if (WANT_F32) accf[k] = fmaf(wn, vv, accf[k]);
+    mbar_wait(&mbar[b], (unsigned)((li >> 1) & 1));
+#define MVF_AX_PASS(WC, REG, W) ax_view_pass<T, WC, REG, WANT_F32>(gt[v], wt[v], plane, dsz, W, ey, ex, S, rS, acc, accf)
+    if (regular) {
+      if (uniform) MVF_AX_PASS(WC_NORMALISED, true, wn_uniform);
+      else if (cls == AW_Z) MVF_AX_PASS(WC_ZTABLE, true, 0.f);
+      else if (cls == AW_3D) MVF_AX_PASS(WC_FIELD, true, 0.f);
+      else MVF_AX_PASS(WC_THREAD, true, wthread);
+    } else {
+      if (uniform) MVF_AX_PASS(WC_NORMALISED, false, wn_uniform);
+      else if (cls == AW_Z) MVF_AX_PASS(WC_ZTABLE, false, 0.f);
+      else if (cls == AW_3D) MVF_AX_PASS(WC_FIELD, false, 0.f);
+      else MVF_AX_PASS(WC_THREAD, false, wthread);
     }
-    __syncthreads();   // every thread is done with this brick buffer
-    if (tid == 0 && li + 2 < nlive) issue(live[li + 2], b);
+#undef MVF_AX_PASS
+    // The buffer goes back to the TMA once every warp has left it; only the issuing thread waits for that, the other
+    // warps move on to the next view (whose brick sits in the other buffer) without a CTA-wide barrier.
+    if (li + 2 < nlive) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&mfree[b]);
+      if (tid == 0) {
+        mbar_wait(&mfree[b], (unsigned)((li >> 1) & 1));
+        issue(live[li + 2], b);
+      }
+    }
   }
 
   const int y = y0 + ty, x = x0 + tx;
   if (y >= X.dims[1] || x >= X.dims[2]) return;
-  uint16_t* out = reinterpret_cast<uint16_t*>(X.out);
+  uint16_t* out = reinterpret_cast<uint16_t*>(X.out) + ((size_t)z0 * X.dims[1] + y) * X.dims[2] + x;
+  float* outf = WANT_F32 ? X.outf + ((size_t)z0 * X.dims[1] + y) * X.dims[2] + x : nullptr;
+  const size_t pl = (size_t)X.dims[1] * X.dims[2];
 #pragma unroll
   for (int k = 0; k < AZ; ++k) {
-    const int z = z0 + k;
-    if (z >= X.dims[0]) break;
-    const size_t idx = ((size_t)z * X.dims[1] + y) * X.dims[2] + x;
-    out[idx] = (uint16_t)(sizeof(T) == 2 ? (acc[k] & 0xFFFFu) : min(acc[k], 65535u));
-    if (WANT_F32) X.outf[idx] = accf[k];
+    if (z0 + k >= X.dims[0]) break;
+    out[k * pl] = (uint16_t)(sizeof(T) == 2 ? (acc[k] & 0xFFFFu) : min(acc[k], 65535u));
+    if (WANT_F32) outf[k * pl] = accf[k];
   }
 }
 
@@ -400,6 +502,7 @@ static bool axis_view(const mvf_view& h, const int32_t dims[3], const int32_t or
   if (av.box[0] > 256 || av.box[1] > 256 || av.box[2] > 256) return false;
   const int str_of[3] = {av.box[1] * av.box[2], av.box[2], 1};
   for (int a = 0; a < 3; ++a) av.str[a] = str_of[av.vax[a]];
+  av.dsz = av.sc[0] > 0 ? av.str[0] : -av.str[0];
   av.bytes = av.box[0] * av.box[1] * av.box[2] * es;
   return av.bytes <= 48 * 1024;
 }
@@ -446,11 +549,24 @@ static int try_fuse_axis(int nviews, const mvf_view* hv, const KArgs& A, cudaStr
     int rc = encode_view_map(hv[v], X.v[v], &TM.m[v]);
     if (rc) return rc;
   }
-  const size_t smem = 2 * (size_t)X.brick_stride;
+  const size_t smem = 2 * (size_t)X.brick_stride + 128;
+  // per-axis tables: stream-ordered scratch, filled by one small kernel in front of the fused kernel
+  const size_t nent = (size_t)nviews * ((size_t)A.dims[0] + A.dims[1] + A.dims[2]);
+  void* scratch = nullptr;
+  MVF_CUDA(cudaMallocAsync(&scratch, nent * (sizeof(GTab) + sizeof(WTab)), st));
+  X.gtab = reinterpret_cast<GTab*>(scratch);
+  X.wtab = reinterpret_cast<WTab*>(X.gtab + nent);
+  ax_tables_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, st>>>(X);
+  mvf::launch_counter()++;
   auto launch = [&](auto kern) -> int {
-    MVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ax_tile_grid(A.dims), ANT, smem, st>>>(TM, X);
-    MVF_LAUNCHED();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      kern<<<ax_tile_grid(A.dims), ANT, smem, st>>>(TM, X);
+      mvf::launch_counter()++;
+      e = cudaGetLastError();
+    }
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(MVF_ERR_CUDA, "%s: %s", "fuse_axis_kernel", cudaGetErrorString(e));
     return MVF_OK;
   };
   *taken = 1;
