@@ -66,6 +66,7 @@ struct AxTile {
   int wcls;    // AW_*
   int corr;    // element offset of brick element (0,0,0) in the absolute offsets of the tables
   int regular; // the z walk never jumps over a plane inside this tile
+  int unit;    // ... and moves on by exactly one plane at every step
 };
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX) ---------------------------------------------------------------
@@ -230,15 +231,14 @@ __device__ __forceinline__ float ax_weight_3d(const WTab& ez, const WTab& ey, co
   return (ez.t >= 0.f && ey.t >= 0.f && ex.t >= 0.f) ? w : 0.f;
 }
 
-enum { WC_NORMALISED = 0, WC_THREAD = 1, WC_ZTABLE = 2, WC_FIELD = 3 };
 
-// One view's contribution to the thread's AZ voxels.  WC selects where the blending weight comes from (one uniform
-// branch per view instead of one per voxel); REGULAR walks are straight-line code (the new plane is always loaded,
-// the plane pair moves by predicated selects), so the loads of step k+1 overlap the arithmetic of step k.
-template <typename T, int WC, bool REGULAR, bool WANT_F32, typename Plane>
-__device__ __forceinline__ void ax_view_pass(const GTab* __restrict__ gz_tab, const WTab* __restrict__ wz_tab, Plane plane, int dsz,
-                                             float wconst, const WTab& ey, const WTab& ex, const float (&S)[AZ],
-                                             const float (&rS)[AZ], uint32_t (&acc)[AZ], float (&accf)[AZ]) {
+// ---- one view's values at the thread's AZ voxels ----------------------------------------------------------------
+// Plane walk: per step the bilinear value of the leading plane is taken from the brick (4 LDS + 6 FP) and the pair
+// (trailing, leading) is carried along.  REGULAR walks (never more than one plane per step) are straight-line code: the
+// new plane is always loaded and the pair moves by predicated selects, so the loads of step k+1 overlap the arithmetic
+// of step k.
+template <bool REGULAR, typename Plane>
+__device__ __forceinline__ void ax_walk_planes(const GTab* __restrict__ gz_tab, Plane plane, int dsz, float (&val)[AZ]) {
   float Pl = 0.f, Pd = plane(gz_tab[0].off - dsz);   // trailing plane of the first step
 #pragma unroll
   for (int k = 0; k < AZ; ++k) {
@@ -252,12 +252,65 @@ __device__ __forceinline__ void ax_view_pass(const GTab* __restrict__ gz_tab, co
       if (gz.mode == 3) { Pl = plane(gz.off - dsz); Pd = plane(gz.off); }
       else if (gz.mode == 1) { Pl = Pd; Pd = plane(gz.off); }
     }
-    float vv = fmaf(gz.t, Pd, gz.omt * Pl);
+    val[k] = fmaf(gz.t, Pd, gz.omt * Pl);
+  }
+}
+
+// Window walk, for float32 views whose z walk runs along the view's contiguous x axis and moves by exactly one element
+// per step (stage rotations of 90 / 270 degrees at ~unit scale).  The lanes of a warp then sit on different view z
+// planes: a 32-bit shared-memory load from a dense TMA brick is at best 4-way bank conflicted (all pitches are
+// multiples of 16 bytes).  16-byte loads are conflict free when pitch/16 is odd (axis_view guarantees it), and the 17
+// elements a thread needs along x are contiguous: 5 LDS.128 per corner row, bilinear reduction on the whole window,
+// then the step values are lerps of neighbouring window elements.  phi = position of the first element inside its
+// 16-byte chunk (uniform over the tile).
+template <bool FWD>
+__device__ __forceinline__ void ax_walk_window(const GTab* __restrict__ gz_tab, const float* __restrict__ p00, const float* __restrict__ p01,
+                                               const float* __restrict__ p10, const float* __restrict__ p11, float tX, float oX,
+                                               float tY, float oY, float (&val)[AZ]) {
+  const int xmin = FWD ? gz_tab[0].off - 1 : gz_tab[AZ - 1].off;   // lowest element of the walk (trailing plane of step 0 / leading plane of the last step)
+  const int c0 = xmin & ~3, phi = xmin & 3;
+  float Q[20];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(p00 + c0 + 4 * c), bb = *reinterpret_cast<const float4*>(p01 + c0 + 4 * c);
+    const float4 cc = *reinterpret_cast<const float4*>(p10 + c0 + 4 * c), d = *reinterpret_cast<const float4*>(p11 + c0 + 4 * c);
+    Q[4 * c + 0] = fmaf(tY, fmaf(tX, d.x, oX * cc.x), oY * fmaf(tX, bb.x, oX * a.x));
+    Q[4 * c + 1] = fmaf(tY, fmaf(tX, d.y, oX * cc.y), oY * fmaf(tX, bb.y, oX * a.y));
+    Q[4 * c + 2] = fmaf(tY, fmaf(tX, d.z, oX * cc.z), oY * fmaf(tX, bb.z, oX * a.z));
+    Q[4 * c + 3] = fmaf(tY, fmaf(tX, d.w, oX * cc.w), oY * fmaf(tX, bb.w, oX * a.w));
+  }
+  // B[i] = Q[i + phi], i = 0..16, by two rounds of uniform selects
+  const bool s1 = (phi & 1) != 0, s2 = (phi & 2) != 0;
+  float A[19];
+#pragma unroll
+  for (int i = 0; i < 19; ++i) A[i] = s1 ? Q[i + 1] : Q[i];
+  float B[17];
+#pragma unroll
+  for (int i = 0; i < 17; ++i) B[i] = s2 ? A[i + 2] : A[i];
+#pragma unroll
+  for (int k = 0; k < AZ; ++k) {
+    const GTab gz = gz_tab[k];   // .t / .omt: weight of the leading / trailing plane
+    const float lead = FWD ? B[k + 1] : B[AZ - 1 - k], trail = FWD ? B[k] : B[AZ - k];
+    val[k] = fmaf(gz.t, lead, gz.omt * trail);
+  }
+}
+
+// ---- weighting and accumulation of one view's values -----------------------------------------------------------
+enum { WC_NORMALISED = 0, WC_THREAD = 1, WC_ZTABLE = 2, WC_FIELD = 3 };
+
+// WC selects where the blending weight comes from (one uniform branch per view instead of one per voxel).
+template <typename T, int WC, bool WANT_F32>
+__device__ __forceinline__ void ax_accumulate(const float (&val)[AZ], const WTab* __restrict__ wz_tab, float wconst, const WTab& ey,
+                                              const WTab& ex, const float (&S)[AZ], const float (&rS)[AZ], uint32_t (&acc)[AZ],
+                                              float (&accf)[AZ]) {
+#pragma unroll
+  for (int k = 0; k < AZ; ++k) {
     float wn;
     if (WC == WC_NORMALISED) wn = wconst;
     else if (WC == WC_THREAD) wn = div_by(wconst, S[k], rS[k]);
     else if (WC == WC_ZTABLE) wn = div_by(wz_tab[k].w1, S[k], rS[k]);
     else wn = div_by(ax_weight_3d(wz_tab[k], ey, ex), S[k], rS[k]);
+    float vv = val[k];
     if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));
     acc[k] += trunc_product_u16(wn, vv);
     if (WANT_F32) accf[k] = fmaf(wn, vv, accf[k]);
@@ -304,10 +357,10 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
       const int ntot = X.dims[0] + X.dims[1] + X.dims[2];
       const int li = z0 + lane;
       for (int v = 0; v < X.nviews; ++v) {
-        bool jump = false;
-        if (lane > 0 && lane < AZ && li < X.dims[0]) jump = (X.gtab[(size_t)v * ntot + li].mode & 3) == 3;
-        const unsigned any = __ballot_sync(0xffffffffu, jump);
-        if (lane == 0) tv[v].regular = any == 0u;
+        int code = 1;   // lanes that are not a step of this tile vote "moved by one"
+        if (lane > 0 && lane < AZ) code = li < X.dims[0] ? (X.gtab[(size_t)v * ntot + li].mode & 3) : 0;
+        const unsigned jumps = __ballot_sync(0xffffffffu, code == 3), ones = __ballot_sync(0xffffffffu, code == 1);
+        if (lane == 0) { tv[v].regular = jumps == 0u; tv[v].unit = ones == 0xffffffffu; }
       }
     }
     __syncwarp();
@@ -405,19 +458,21 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
       return fmaf(tY, r1, oY * r0);
     };
     mbar_wait(&mbar[b], (unsigned)((li >> 1) & 1));
-#define MVF_AX_PASS(WC, REG, W) ax_view_pass<T, WC, REG, WANT_F32>(gt[v], wt[v], plane, dsz, W, ey, ex, S, rS, acc, accf)
-    if (regular) {
-      if (uniform) MVF_AX_PASS(WC_NORMALISED, true, wn_uniform);
-      else if (cls == AW_Z) MVF_AX_PASS(WC_ZTABLE, true, 0.f);
-      else if (cls == AW_3D) MVF_AX_PASS(WC_FIELD, true, 0.f);
-      else MVF_AX_PASS(WC_THREAD, true, wthread);
+    float val[AZ];
+    if (sizeof(T) == 4 && sX != 1 && av.str[0] == 1 && tv[v].unit) {   // z walk along the view's x: conflict-free 16-byte window loads
+      const float *q00 = reinterpret_cast<const float*>(p00), *q01 = reinterpret_cast<const float*>(p01),
+                  *q10 = reinterpret_cast<const float*>(p10), *q11 = reinterpret_cast<const float*>(p11);
+      if (dsz > 0) ax_walk_window<true>(gt[v], q00, q01, q10, q11, tX, oX, tY, oY, val);
+      else ax_walk_window<false>(gt[v], q00, q01, q10, q11, tX, oX, tY, oY, val);
+    } else if (regular) {
+      ax_walk_planes<true>(gt[v], plane, dsz, val);
     } else {
-      if (uniform) MVF_AX_PASS(WC_NORMALISED, false, wn_uniform);
-      else if (cls == AW_Z) MVF_AX_PASS(WC_ZTABLE, false, 0.f);
-      else if (cls == AW_3D) MVF_AX_PASS(WC_FIELD, false, 0.f);
-      else MVF_AX_PASS(WC_THREAD, false, wthread);
+      ax_walk_planes<false>(gt[v], plane, dsz, val);
     }
-#undef MVF_AX_PASS
+    if (uniform) ax_accumulate<T, WC_NORMALISED, WANT_F32>(val, wt[v], wn_uniform, ey, ex, S, rS, acc, accf);
+    else if (cls == AW_Z) ax_accumulate<T, WC_ZTABLE, WANT_F32>(val, wt[v], 0.f, ey, ex, S, rS, acc, accf);
+    else if (cls == AW_3D) ax_accumulate<T, WC_FIELD, WANT_F32>(val, wt[v], 0.f, ey, ex, S, rS, acc, accf);
+    else ax_accumulate<T, WC_THREAD, WANT_F32>(val, wt[v], wthread, ey, ex, S, rS, acc, accf);
     // The buffer goes back to the TMA once every warp has left it; only the issuing thread waits for that, the other
     // warps move on to the next view (whose brick sits in the other buffer) without a CTA-wide barrier.
     if (li + 2 < nlive) {
