@@ -177,6 +177,8 @@ int mvf_rl_correct(const float* ratio, const int32_t* zmap, const int32_t dims[3
  * includes the halo planes), mvf_rl_*_z run the z pass through the plane map on that intermediate and apply the
  * same epilogues as mvf_rl_blur / mvf_rl_ratio / mvf_rl_correct.  Two kernels without shared memory or barriers
  * replace one fused kernel; the intermediate costs one extra float32 round trip through HBM.
+ * mvf_rl_ratio_z accepts weights == NULL when the caller has already zeroed the view wherever w <= 1e-5 (I = 0 makes
+ * the ratio exactly 0 there, which is all the mask of mv:5636, 5695-5699 does): the pass then reads 4 bytes less per voxel.
  * mvf_rl_stream_supported: 1 if the PSF is separable and dims[2] is a multiple of the vector width (4 columns up
  * to 19 taps, 2 beyond). */
 int mvf_rl_stream_supported(const int32_t dims[3], const mvf_rl_psf* psf);

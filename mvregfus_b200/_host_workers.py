@@ -20,6 +20,25 @@ def probe_flags(orig_props, p, stack_properties, n_points):
     return flags
 
 
+def probe_any_inside_blocks(orig_props, p, origins, size, spacing, n_points):
+    """`probe_flags(...).any()` for many target boxes of one size at once (origins: (B, 3) physical corners): the
+    probe-point early-out of get_weights_simple (mv:3491-3532) for every 128^3 block of a volume.  Same arithmetic per
+    point, evaluated column-wise on all points of all boxes."""
+    rel = np.linspace(0, 1, n_points)
+    grid = np.stack(np.meshgrid(rel, rel, rel, indexing="ij"), -1).reshape(-1, 3)              # (P, 3)
+    origins = np.asarray(origins, dtype=np.float64)
+    phys = origins[:, None, :] + grid[None, :, :] * np.asarray(size) * np.asarray(spacing)     # (B, P, 3)
+    p = np.asarray(p, dtype=np.float64)
+    A, c = p[:9].reshape(3, 3), p[9:]
+    inside = np.ones(phys.shape[:2], dtype=bool)
+    vsize = np.asarray(orig_props["size"])
+    for d in range(3):
+        y = A[d, 0] * phys[..., 0] + A[d, 1] * phys[..., 1] + A[d, 2] * phys[..., 2]
+        pix = (y + c[d] - orig_props["origin"][d]) / orig_props["spacing"][d]
+        inside &= (pix >= 0) & (pix < vsize[d])
+    return inside.any(axis=1)
+
+
 def blocks_inside_codes(orig_stack_propertiess, params, stack_properties, n_points_per_dim=5):
     """1 all probe points inside / 0 none / 2 partial, per view (mv:3406-3466)."""
     codes = []

@@ -394,41 +394,12 @@ static int launch_rl_k(const RLArgs& A, cudaStream_t st) {
 }
 
 }  // namespace mvf
-#include "rl_pair.cuh"
 #include "rl_stream.cuh"
 namespace mvf {
-
-// MVF_RL_KERNEL=v2 selects the FFMA2 plane-pair kernel (rl_pair.cuh) for PSFs up to 19 taps; the default is the
-// scalar-FFMA kernel above, which is as fast (31.7 vs 32.3 ms/iteration on C4) and covers all sizes.
-// MVF_RL_CFG picks a tile configuration of the pair kernel (tuning builds, -DMVF_RL_TUNE)
-static int rl_env(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e + (e[0] == 'v')) : dflt;
-}
-
-template <int K, int MODE>
-static int launch_rl_pair(const RLArgs& A, cudaStream_t st) {
-  switch (rl_env("MVF_RL_CFG", 1)) {
-#ifdef MVF_RL_TUNE
-    case 0: return launch_rl_pair_cfg<K, MODE, 32, 4, 8>(A, st);
-    case 2: return launch_rl_pair_cfg<K, MODE, 64, 4, 8>(A, st);
-    case 3: return launch_rl_pair_cfg<K, MODE, 32, 2, 8>(A, st);
-    case 4: return launch_rl_pair_cfg<K, MODE, 64, 2, 8>(A, st);
-#endif
-    default: return launch_rl_pair_cfg<K, MODE, 48, 4, 8>(A, st);
-  }
-}
 
 template <int MODE>
 static int launch_rl(int kp, const RLArgs& A, cudaStream_t st) {
   if (A.dense) return launch_rl_direct<MODE>(kp, A, st);
-  if (kp <= 19 && rl_env("MVF_RL_KERNEL", 1) == 2 && (long long)A.ny * A.nx < (1LL << 28)) {
-    switch (kp) {
-      case 7: return launch_rl_pair<7, MODE>(A, st);
-      case 13: return launch_rl_pair<13, MODE>(A, st);
-      case 19: return launch_rl_pair<19, MODE>(A, st);
-    }
-  }
   switch (kp) {
     case 7: return launch_rl_k<7, MODE, 4>(A, st);
     case 13: return launch_rl_k<13, MODE, 4>(A, st);
@@ -609,7 +580,7 @@ extern "C" int mvf_rl_ratio_z(const float* in, const int32_t* zmap, const int32_
   int kp;
   int rc = fill_rl(A, in, zmap, dims, psf, &kp);
   if (rc) return rc;
-  MVF_CHECK_ARG(view && weights && ratio_out, "NULL argument");
+  MVF_CHECK_ARG(view && ratio_out, "NULL argument");   // weights may be NULL: view already zeroed where w <= 1e-5
   MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
   A.view = view; A.view_u16 = dtype == MVF_U16; A.weights = weights; A.out = ratio_out;
   // a uint16 view moves as 2 * CW bytes per thread: checking it with a doubled address applies the halved requirement

@@ -190,8 +190,11 @@ template <int K, int MODE, int CW>
 __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid_constant__ RLArgs A) {
   constexpr int R = (K - 1) / 2;
   const size_t plane = (size_t)A.ny * A.nx;
-  const size_t i0 = ((size_t)blockIdx.x * RLS_NT + threadIdx.x) * CW;   // first voxel of the thread inside a plane
-  if (i0 >= plane) return;
+  // Threads beyond the plane (last CTA) stay alive - the block sum below shuffles across the full warp - but work on
+  // voxel 0 of the plane and neither store nor count.
+  const size_t i0raw = ((size_t)blockIdx.x * RLS_NT + threadIdx.x) * CW;   // first voxel of the thread inside a plane
+  const bool active = i0raw < plane;
+  const size_t i0 = active ? i0raw : 0;
   const int zo0 = blockIdx.y * A.zchunk, zo1 = min(A.nz, zo0 + A.zchunk);
   const int* __restrict__ zmap = A.zmap + R;    // zmap[t], t in [-R, nz + R)
   float S[CW][K - 1];
@@ -209,9 +212,14 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
   float p[CW], pn[CW];
   float eW[CW], eC[CW], eI[CW];
   unsigned eRaw[2] = {0u, 0u};   // uint16 view voxels stay packed until they are used
+  // ratio mode with weights == NULL: the caller has zeroed the view wherever w <= 1e-5 (I = 0 gives R = 0 exactly),
+  // so the mask costs no 4-byte read per voxel
+  const bool have_w = wts != nullptr;
+#pragma unroll
+  for (int i = 0; i < CW; ++i) eW[i] = 1.f;
   auto load_operands = [&](int z) {
     const size_t o = (size_t)z * plane + i0;
-    vec_load<CW>(wts + o, eW);
+    if (have_w) vec_load<CW>(wts + o, eW);
     if (MODE == RL_RATIO) {
       if (A.view_u16) {
         const uint16_t* vp = reinterpret_cast<const uint16_t*>(A.view) + o;
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
       prefetch_l2(A.in + (size_t)__ldg(zmap + t + RLS_AHEAD) * plane + i0);
       if (MODE != RL_PLAIN && z + RLS_AHEAD >= zo0) {   // epilogue operands of the plane completed RLS_AHEAD steps from now
         const size_t oa = o + (size_t)RLS_AHEAD * plane;
-        prefetch_l2(wts + oa);
+        if (have_w) prefetch_l2(wts + oa);
         if (MODE == RL_RATIO) prefetch_l2(reinterpret_cast<const unsigned char*>(A.view) + oa * (A.view_u16 ? 2 : 4));
         if (MODE == RL_CORRECT && !A.first) prefetch_l2(outp + oa);
         if (MODE == RL_CORRECT && A.last) prefetch_l2(est + oa);
@@ -280,13 +288,13 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
           const float corr = A.first ? ow : eC[i] + ow;
           if (A.last) {
             r[i] = fminf(fmaxf(eI[i] * corr, 0.f), 65535.f);
-            local_sum += (double)r[i];
+            if (active) local_sum += (double)r[i];
           } else {
             r[i] = corr;
           }
         }
       }
-      vec_store<CW>((MODE == RL_CORRECT && A.last) ? est + o : outp + o, r);
+      if (active) vec_store<CW>((MODE == RL_CORRECT && A.last) ? est + o : outp + o, r);
     }
     // operands of the plane the next step completes
     if (MODE != RL_PLAIN && z + 1 >= zo0 && z + 1 < zo1) load_operands(z + 1);

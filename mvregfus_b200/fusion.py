@@ -30,7 +30,8 @@ def dtype_code(t):
 
 
 def to_device(arr, device=None):
-    """numpy (uint16/float32, any layout) -> contiguous CUDA tensor."""
+    """numpy (uint16/float32, any layout) -> contiguous CUDA tensor.  Page-locked host memory (``pinned_empty``) is
+    copied asynchronously on the current stream; pageable memory goes through the driver's staging copy."""
     require_cuda()
     arr = np.ascontiguousarray(np.asarray(arr))
     if arr.dtype not in _TORCH_DT:
@@ -38,7 +39,24 @@ def to_device(arr, device=None):
             arr = arr.astype(np.float32)
         else:
             raise TypeError("unsupported voxel dtype %s (uint16 and float32 are supported)" % arr.dtype)
-    return torch.from_numpy(arr).to(device or "cuda", non_blocking=False)
+    t = torch.from_numpy(arr)
+    return t.to(device or "cuda", non_blocking=t.is_pinned())
+
+
+def pinned_empty(shape, dtype):
+    """Host ndarray in page-locked memory (the tensor that owns it stays alive through ``ndarray.base``): what a caller
+    should hand to the drop-in entry points when PCIe time matters."""
+    require_cuda()
+    return torch.empty(tuple(int(s) for s in shape), dtype=_TORCH_DT[np.dtype(dtype)][0], pin_memory=True).numpy()
+
+
+def to_host(t):
+    """CUDA tensor -> host ndarray through a page-locked buffer (torch's caching host allocator recycles them), so
+    the D2H copy runs at link speed instead of through the pageable staging path."""
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy()
 
 
 def _stream_ptr():
@@ -56,7 +74,30 @@ def probe_any_inside(orig_props, p, stack_properties, n_points=5):
 from ._host_workers import blocks_inside_codes, probe_flags as _probe_flags  # noqa: E402,F401  (torch-free implementation)
 
 
+_PROFILE_CACHE = {}
+
+
 def border_profiles(orig_props):
+    """Cached :func:`_border_profiles` (the profiles depend on the view's size and spacing only)."""
+    key = (tuple(int(x) for x in orig_props["size"]), tuple(float(x) for x in orig_props["spacing"]))
+    hit = _PROFILE_CACHE.get(key)
+    if hit is None:
+        if len(_PROFILE_CACHE) > 256:
+            _PROFILE_CACHE.clear()
+        hit = _PROFILE_CACHE[key] = _border_profiles(orig_props)
+    return hit
+
+
+def _profile_tensor(orig_props, prof, dev):
+    """Device copy of a view's border profiles, uploaded once per (view geometry, device)."""
+    key = (tuple(int(x) for x in orig_props["size"]), tuple(float(x) for x in orig_props["spacing"]), str(dev))
+    hit = _PROFILE_CACHE.get(key)
+    if hit is None:
+        hit = _PROFILE_CACHE[key] = torch.from_numpy(prof.ravel().copy()).to(dev)
+    return hit
+
+
+def _border_profiles(orig_props):
     """1-D profiles (3, 200) float32 of the sigmoid-border field and the field spacing.
 
     The reference fills a 200^3 array slab by slab with ``min(sigmoid(bx), slab)`` (mv:3577-3598); the
@@ -141,7 +182,7 @@ def build_viewset(tensors, orig_stack_propertiess, params, stack_properties, wei
         lo_hi = [_ones_range(prof[d]) for d in range(3)]
         s.one_lo = _cabi.i32x3([a for a, _ in lo_hi])
         s.one_hi = _cabi.i32x3([b for _, b in lo_hi])
-        pt = torch.from_numpy(prof.ravel().copy()).to(dev)
+        pt = _profile_tensor(osp, prof, dev)
         vs.keep.append(pt)
         s.profiles = pt.data_ptr()
         s.weight_mode = _cabi.MVF_W_BLEND

@@ -9,6 +9,7 @@ Host arrays in, host arrays out (the reference's contract); the device-resident 
 PCIe round trip per call is ``mvregfus_b200.fusion`` / ``mvregfus_b200.pipeline``.
 """
 import numpy as np
+import torch
 
 from . import fusion
 from .image_array import ImageArray
@@ -84,10 +85,46 @@ def _resample_host(stack, p, out_shape, out_origin, out_spacing, rule):
     dims = [int(np.ceil(s)) for s in out_shape]
     src = fusion.to_device(stack)
     res = fusion.affine_resample(src, matrix, offset, dims, (0, 0, 0), rule=rule)
-    out = res.cpu().numpy()
+    out = fusion.to_host(res)
     if out.dtype != np.asarray(stack).dtype and np.issubdtype(np.asarray(stack).dtype, np.floating):
         out = out.astype(np.asarray(stack).dtype)
     return out
+
+
+class LazyTransformedView:
+    """Result of :func:`transform_stack_dask_numpy`.  The reference returns a *lazy* dask array there (mv:1458-1519):
+    nothing is resampled until a consumer pulls chunks.  This object keeps that contract without dask - it knows its
+    ``shape`` / ``dtype`` / ``spacing`` / ``origin``, materialises on ``np.asarray()`` / indexing / ``compute()`` (one
+    K1 launch for the whole volume, cached), and lets :func:`fuse_blockwise_arrays` fuse straight from the raw views
+    when every input is still lazy, so the transformed views never exist in host memory."""
+
+    def __init__(self, stack, p, out_shape, out_origin, out_spacing, chunksize):
+        self.stack, self.p = stack, np.array(p, dtype=np.float64)
+        self.shape = tuple(int(np.ceil(x)) for x in out_shape)
+        self.spacing = np.array(out_spacing, dtype=np.float64)
+        self.origin = np.array(out_origin, dtype=np.float64)
+        self.dtype = np.asarray(stack).dtype
+        self.ndim = len(self.shape)
+        self.chunks = tuple([int(chunksize)] * self.ndim)
+        self._value = None
+
+    def compute(self):
+        if self._value is None:
+            self._value = _resample_host(self.stack, self.p, self.shape, self.origin, self.spacing, "scipy")
+        return self._value
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.compute()
+        return v if dtype is None else v.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.compute()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def max(self, *a, **k):
+        return self.compute().max(*a, **k)
 
 
 def transform_stack_sitk(stack, p=None, out_shape=None, out_spacing=None, out_origin=None, interp="linear",
@@ -116,12 +153,18 @@ def transform_stack_dask_numpy(stack, p=None, out_shape=None, out_spacing=None, 
                                stack_properties=None, chunksize=512):
     """scipy-rule order-1 resampling of a view into the fused frame (mv:1458-1519).
 
-    The reference returns a lazy dask array that evaluates ``scipy.ndimage.affine_transform(order=1)``
-    per chunk; here the whole volume is resampled by one kernel launch and, if dask is installed, wrapped
-    with ``da.from_array(..., chunks=chunksize)`` to keep the dask contract."""
+    The reference returns a lazy dask array that evaluates ``scipy.ndimage.affine_transform(order=1)`` per chunk;
+    here a :class:`LazyTransformedView` (wrapped with ``da.from_array`` when dask is installed) that resamples the
+    whole volume with one kernel launch the first time its voxels are asked for."""
     out_shape, out_origin, out_spacing = _out_geometry(stack, out_shape, out_spacing, out_origin, stack_properties)
-    res = _resample_host(stack, np.array(p), out_shape, out_origin, out_spacing, "scipy")
-    return _maybe_dask(res, [chunksize] * stack.ndim)
+    if not hasattr(stack, "spacing"):
+        stack = ImageArray(stack)
+    lazy = LazyTransformedView(stack, p, out_shape, out_origin, out_spacing, chunksize)
+    try:
+        import dask.array as da
+    except ImportError:
+        return lazy
+    return da.from_array(lazy, chunks=lazy.chunks)   # dask pulls through __getitem__: still lazy
 
 
 def affine_transform_dask(input, matrix, offset=0.0, output_shape=None, output_chunks=(128, 128, 128), **kwargs):
@@ -134,7 +177,7 @@ def affine_transform_dask(input, matrix, offset=0.0, output_shape=None, output_c
     offset = np.broadcast_to(np.asarray(offset, dtype=np.float64), (3,))
     src = fusion.to_device(input)
     res = fusion.affine_resample(src, matrix, offset, [int(s) for s in output_shape], (0, 0, 0), rule="scipy")
-    return _maybe_dask(res.cpu().numpy(), output_chunks)
+    return _maybe_dask(fusion.to_host(res), output_chunks)
 
 
 def transform_view_dask_and_save_chunked(fn, view, params, iview, stack_properties, chunksize=128):
@@ -167,7 +210,7 @@ def get_weights_simple(orig_stack_propertiess, params, stack_properties):
     (mv:3469-3633).  Returns a list of V float32 arrays like the reference."""
     dims = [int(s) for s in stack_properties["size"]]
     vs = fusion.build_viewset(None, orig_stack_propertiess, params, stack_properties, weights="blending")
-    w = fusion.blend_weights(vs, dims, (0, 0, 0), normalise=True).cpu().numpy()
+    w = fusion.to_host(fusion.blend_weights(vs, dims, (0, 0, 0), normalise=True))
     return [ImageArray(w[i], origin=stack_properties["origin"], spacing=stack_properties["spacing"])
             for i in range(len(params))]
 
@@ -186,32 +229,45 @@ def fuse_views_weights(views, params, stack_properties, weights=None, views_in_t
         if i0:                           # for uint16 views; keep the reference contract for the common case
             raise Exception("fuse_views_weights: more than 8 views are not supported by one fused pass")
         out = fusion.fuse_weighted(dviews[i0:i0 + 8], dweights[i0:i0 + 8] if dweights is not None else None)
-    return ImageArray(out.cpu().numpy(), spacing=stack_properties["spacing"], origin=stack_properties["origin"])
+    return ImageArray(fusion.to_host(out), spacing=stack_properties["spacing"], origin=stack_properties["origin"])
 
 
 # ---------------------------------------------------------------------------------------------------
 # a14/a15: PSF and multi-view Richardson-Lucy
 # ---------------------------------------------------------------------------------------------------
+_PSF_CACHE = {}
+
+
 def get_psf(p, stack_properties, sz, sxy):
-    """Gaussian PSF of a view in the fused frame (mv:5376-5418): a delta filtered with sigma (sz, sxy, sxy),
-    rotated by the view's affine (translation dropped) with ITK-linear resampling, normalised, float32.
-    Host arithmetic (a (3*max sigma)^3 array) except for the rotation, which runs through K1."""
+    """Gaussian PSF of a view in the fused frame (mv:5376-5418), float32, normalised to sum 1.
+
+    Extent per axis: ``int(max(1, 3 * max(sz, sxy)) / spacing)`` made odd; a centred delta is blurred with
+    ``sigma = (sz, sxy, sxy) / spacing`` (scipy's reflect mode, as the reference) and rotated about the centre by the
+    linear part of the view's affine with ITK-rule linear resampling (K1).  Cached per (linear part, spacing, sigmas):
+    every 128^3 block of a fusion asks for the same PSFs."""
     from scipy import ndimage
     spacing = np.asarray(stack_properties['spacing'], dtype=np.float64)
-    psf_shape = (np.array([np.max([1, np.max([sz, sxy, sxy]) * 3])]) / spacing).astype(np.int64)
-    psf_shape = np.array([ps + [1, 0][int(ps % 2)] for ps in psf_shape]).astype(np.int64)  # odd
-    psf_orig = np.zeros(psf_shape, dtype=np.float32)
-    psf_orig[psf_shape[0] // 2, psf_shape[1] // 2, psf_shape[2] // 2] = 1
-    psf_orig = ndimage.gaussian_filter(psf_orig, np.array([sz, sxy, sxy]) / spacing)
-    origin = -spacing * (psf_shape // 2)
-    psf_orig = ImageArray(psf_orig, spacing=spacing, origin=origin)
-    tmpp = np.copy(np.asarray(p, dtype=np.float64))
-    tmpp[-3:] = 0
-    psf_target = transform_stack_sitk(psf_orig, tmpp, out_origin=origin, out_shape=psf_shape, out_spacing=spacing,
-                                      interp='linear')
-    psf_target = np.asarray(psf_target)
-    psf_target = psf_target / np.sum(psf_target)
-    return psf_target.astype(np.float32)
+    linear = np.asarray(p, dtype=np.float64)[:9]
+    key = (tuple(linear), tuple(spacing), float(sz), float(sxy))
+    hit = _PSF_CACHE.get(key)
+    if hit is not None:
+        return hit.copy()
+    sigmas = np.array([sz, sxy, sxy], dtype=np.float64)
+    extent = (np.array([max(1, 3 * sigmas.max())]) / spacing).astype(np.int64)
+    extent = extent + (1 - extent % 2)          # even extents grow by one voxel
+    centre = extent // 2
+    delta = np.zeros(extent, dtype=np.float32)
+    delta[tuple(centre)] = 1
+    corner = -spacing * centre                  # physical position of voxel 0: the delta sits at the origin
+    gauss = ImageArray(ndimage.gaussian_filter(delta, sigmas / spacing), spacing=spacing, origin=corner)
+    rotation_only = np.concatenate([linear, np.zeros(3)])
+    rotated = np.asarray(transform_stack_sitk(gauss, rotation_only, out_origin=corner, out_shape=extent,
+                                              out_spacing=spacing, interp='linear'))
+    psf = (rotated / np.sum(rotated)).astype(np.float32)
+    if len(_PSF_CACHE) > 64:
+        _PSF_CACHE.clear()
+    _PSF_CACHE[key] = psf
+    return psf.copy()
 
 
 def fuse_LR_with_weights_np(views, params, stack_properties, num_iterations=25, sz=4, sxy=0.5, tol=5e-5,
@@ -223,8 +279,8 @@ def fuse_LR_with_weights_np(views, params, stack_properties, num_iterations=25, 
     dweights = [fusion.to_device(np.asarray(w, dtype=np.float32)) for w in weights]
     plan = rl.RLPlan(dviews, dweights, psfs)
     est = plan.run(num_iterations=num_iterations, tol=tol)
-    est = est.cpu().numpy()
-    return ImageArray(est.astype(np.uint16), spacing=stack_properties['spacing'], origin=stack_properties['origin'])
+    est = fusion.to_host(est.to(torch.int32).to(torch.uint16))   # float32 -> uint16 truncates like ndarray.astype (values are clipped to [0, 65535])
+    return ImageArray(est, spacing=stack_properties['spacing'], origin=stack_properties['origin'])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -305,102 +361,115 @@ def get_weights_dct(views, params, orig_stack_propertiess, stack_properties, siz
 # ---------------------------------------------------------------------------------------------------
 # a16: block orchestration
 # ---------------------------------------------------------------------------------------------------
+def _live(values):
+    """Indices whose maximum is positive: fuse_block keeps a view (or its weights) only if it has signal in the block."""
+    return [i for i, x in enumerate(values) if x.max() > 0]
+
+
+def _block_frame(stack_properties, block_shape, chunk_location, array_info):
+    """stack_properties of one (overlapping) chunk: origin moved by ``chunk_location * chunksize - depth`` voxels."""
+    shift = np.array(chunk_location, dtype=np.float64) * array_info['chunksize'] - array_info['depth']
+    frame = dict(stack_properties)
+    frame['size'] = np.array(block_shape)
+    frame['origin'] = np.asarray(stack_properties['origin'], dtype=np.float64) + shift * np.asarray(stack_properties['spacing'])
+    return frame
+
+
 def fuse_block(tviews_block, weights, params, stack_properties, orig_stack_propertiess, array_info, weights_func,
                fusion_func, weights_kwargs, fusion_kwargs, block_info=None):
-    """Fuse one (V, 128+2d, ...) block (mv:3817-3916): drop views that are empty in the block, return the raw block
-    of the only live view (or view 0) in the trivial cases, compute the block origin from the chunk location,
-    call ``weights_func`` / ``fusion_func`` by keyword."""
-    max_vals = np.array([tview_block.max() for tview_block in tviews_block])
-    inds = np.where(max_vals > 0)[0]
-    if len(inds) == 0:
-        return tviews_block[0]
-    elif len(inds) == 1:
-        return tviews_block[inds[0]]
-    tviews_block = tviews_block[inds]
-    params = np.array(params)[inds]
-    orig_stack_propertiess = [orig_stack_propertiess[i] for i in inds]
-    ndim = len(orig_stack_propertiess[0]['spacing'])
-    curr_origin = []
-    for i in range(ndim):
-        pixel_offset = block_info[0]['chunk-location'][i + 1] * array_info['chunksize'] - array_info['depth']
-        curr_origin.append(stack_properties['origin'][i] + pixel_offset * stack_properties['spacing'][i])
-    block_stack_properties = stack_properties.copy()
-    block_stack_properties['size'] = np.array(tviews_block[0].shape)
-    block_stack_properties['origin'] = np.array(curr_origin)
-    tviews = [ImageArray(t, spacing=block_stack_properties['spacing'], origin=block_stack_properties['origin'])
-              for t in tviews_block]
-    weights_kwargs['stack_properties'] = block_stack_properties
-    fusion_kwargs['stack_properties'] = block_stack_properties
-    weights_kwargs['params'] = params
-    fusion_kwargs['params'] = params
-    if 'orig_stack_propertiess' in weights_func.__code__.co_varnames:
-        weights_kwargs['orig_stack_propertiess'] = orig_stack_propertiess
-    if 'orig_stack_propertiess' in fusion_func.__code__.co_varnames:
-        fusion_kwargs['orig_stack_propertiess'] = orig_stack_propertiess
-    if weights is None and weights_func == get_weights_simple and fusion_func in (fuse_views_weights, fuse_LR_with_weights_np):
-        # device-resident fast path: same control flow, but the block's weights never travel over PCIe
-        return _fuse_block_device(tviews_block, tviews, params, orig_stack_propertiess, block_stack_properties,
-                                  fusion_func, fusion_kwargs)
-    if weights is None and weights_func == get_weights_simple:
+    """Fuse one (V, 128+2d, ...) block of transformed views (mv:3817-3916).
+
+    Block semantics of the reference: views without signal in the block are dropped; with no or one view left the raw
+    block of view 0 / of that view is the result; the block's frame follows from its chunk location; the weight and
+    fusion functions are called by keyword and only receive ``orig_stack_propertiess`` when they name it; views whose
+    weights vanish on the block are judged the same way a second time."""
+    keep = _live(tviews_block)
+    if len(keep) < 2:
+        return tviews_block[keep[0] if keep else 0]
+    block_views = tviews_block[keep]
+    params = np.array(params)[keep]
+    view_frames = [orig_stack_propertiess[i] for i in keep]
+    frame = _block_frame(stack_properties, block_views[0].shape, block_info[0]['chunk-location'][1:], array_info)
+    for kwargs, func in ((weights_kwargs, weights_func), (fusion_kwargs, fusion_func)):
+        kwargs['stack_properties'] = frame
+        kwargs['params'] = params
+        if 'orig_stack_propertiess' in func.__code__.co_varnames:
+            kwargs['orig_stack_propertiess'] = view_frames
+    tviews = [ImageArray(t, spacing=frame['spacing'], origin=frame['origin']) for t in block_views]
+    blending = weights is None and weights_func == get_weights_simple
+    if blending and fusion_func in (fuse_views_weights, fuse_LR_with_weights_np):
+        # device-resident: same decisions, but the block's weights never travel over PCIe
+        return _fuse_block_device(block_views, params, view_frames, frame, fusion_func, fusion_kwargs)
+    if blending:
         weights = weights_func(**weights_kwargs)
     else:
-        weights = [ImageArray(w, spacing=block_stack_properties['spacing'], origin=block_stack_properties['origin'])
-                   for iw, w in enumerate(weights) if iw in inds]
-    max_vals = np.array([w.max() for w in weights])
-    inds = np.where(max_vals > 0)[0]
-    if len(inds) == 0:
-        return tviews_block[0]
-    elif len(inds) == 1:
-        return tviews_block[inds[0]]
+        weights = [ImageArray(weights[i], spacing=frame['spacing'], origin=frame['origin']) for i in keep]
+    weighted = _live(weights)
+    if len(weighted) < 2:
+        return block_views[weighted[0] if weighted else 0]
     return fusion_func(tviews, weights=weights, **fusion_kwargs)
 
 
-def _fuse_block_device(tviews_block, tviews, params, orig_stack_propertiess, block_stack_properties, fusion_func,
-                       fusion_kwargs):
-    """Second half of fuse_block (mv:3876-3911) with the blending weights computed and consumed on the device:
-    weights -> drop views whose weights vanish on the block -> trivial cases return the raw view block ->
-    fuse_views_weights / fuse_LR_with_weights_np arithmetic on device tensors -> one D2H of the fused block."""
+def _fuse_block_device(block_views, params, view_frames, frame, fusion_func, fusion_kwargs):
+    """The tail of fuse_block (mv:3876-3911) for blending weights, on device tensors: weights -> views whose weights
+    vanish decide the trivial cases -> weighted average or Richardson-Lucy -> one D2H of the fused block."""
     from . import rl
-    dims = [int(s) for s in block_stack_properties['size']]
-    vs = fusion.build_viewset(None, orig_stack_propertiess, params, block_stack_properties, weights="blending")
+    dims = [int(s) for s in frame['size']]
+    vs = fusion.build_viewset(None, view_frames, params, frame, weights="blending")
     w = fusion.blend_weights(vs, dims, (0, 0, 0), normalise=True)
-    wmax = w.reshape(w.shape[0], -1).amax(dim=1).cpu().numpy()
-    inds = np.where(wmax > 0)[0]
-    if len(inds) == 0:
-        return tviews_block[0]
-    elif len(inds) == 1:
-        return tviews_block[inds[0]]
-    dviews = [fusion.to_device(t) for t in tviews_block]
-    dweights = [w[i] for i in range(w.shape[0])]
-    sp = block_stack_properties
+    weighted = np.where(w.reshape(w.shape[0], -1).amax(dim=1).cpu().numpy() > 0)[0]
+    if len(weighted) < 2:
+        return block_views[weighted[0] if len(weighted) else 0]
+    dviews = [fusion.to_device(t) for t in block_views]
+    dweights = list(w.unbind(0))
     if fusion_func == fuse_views_weights:
-        out = fusion.fuse_weighted(dviews, dweights).cpu().numpy()
-        return ImageArray(out, spacing=sp['spacing'], origin=sp['origin'])
-    kw = dict(fusion_kwargs)
-    psfs = [get_psf(params[ip], sp, kw.get('sz', 4), kw.get('sxy', 0.5)) for ip in range(len(params))]
-    est = rl.RLPlan(dviews, dweights, psfs).run(num_iterations=kw.get('num_iterations', 25), tol=kw.get('tol', 5e-5))
-    return ImageArray(est.cpu().numpy().astype(np.uint16), spacing=sp['spacing'], origin=sp['origin'])
+        return ImageArray(fusion.to_host(fusion.fuse_weighted(dviews, dweights)), spacing=frame['spacing'], origin=frame['origin'])
+    opt = dict(fusion_kwargs)
+    psfs = [get_psf(q, frame, opt.get('sz', 4), opt.get('sxy', 0.5)) for q in params]
+    est = rl.RLPlan(dviews, dweights, psfs).run(num_iterations=opt.get('num_iterations', 25), tol=opt.get('tol', 5e-5))
+    return ImageArray(fusion.to_host(est.to(torch.int32).to(torch.uint16)), spacing=frame['spacing'], origin=frame['origin'])
 
 
 def _overlap_block(sources, loc, depth, chunk):
-    """overlap_from_sources (mv:3662-3707) for one chunk location: reflect padding at the volume edges."""
-    srcshape = np.array(sources[0].shape)
-    ys = np.zeros([len(sources)] + [chunk + 2 * depth] * 3, dtype=sources[0].dtype)
-    pads, slices = [], []
-    for d in range(3):
-        lo, up = loc[d] * chunk, (loc[d] + 1) * chunk
-        if lo >= srcshape[d]:
-            return ys
-        udiff = srcshape[d] - up
-        pads.append([depth if lo == 0 else 0, depth - udiff if udiff < depth else 0])
-        slices.append(slice(max(0, lo - depth), min(srcshape[d], up + depth)))
-    pads = np.array(pads)
-    for iv, src in enumerate(sources):
-        y = np.array(src[tuple(slices)])
-        if pads.max() > 0:
-            y = np.pad(y, pads, mode='reflect')
-        ys[iv] = y
-    return ys
+    """One chunk of every source with a ``depth`` halo (overlap_from_sources, mv:3662-3707): the halo comes from the
+    neighbouring voxels inside the volume and from a reflection at its faces; chunks beyond the volume are zeros."""
+    extent = np.array(sources[0].shape)
+    first = np.array(loc) * chunk
+    block = np.zeros((len(sources),) + (chunk + 2 * depth,) * 3, dtype=sources[0].dtype)
+    if np.any(first >= extent):
+        return block
+    last = first + chunk
+    window = tuple(slice(int(max(0, a - depth)), int(min(n, b + depth))) for a, b, n in zip(first, last, extent))
+    # a face of the volume inside the halo -> reflect what is missing there
+    missing = [(depth if a == 0 else 0, int(max(0, depth - (n - b)))) for a, b, n in zip(first, last, extent)]
+    for i, src in enumerate(sources):
+        part = np.array(src[window])
+        block[i] = np.pad(part, missing, mode='reflect') if np.any(missing) else part
+    return block
+
+
+def _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_propertiess):
+    """fuse_blockwise for blending weights + weighted average at overlap 0 when every transformed view is still
+    lazy: the raw views go to the device once, one fused launch applies fuse_block's per-chunk decisions
+    (mvregfus_b200.pipeline), the fused volume comes back once.  None if the inputs do not qualify."""
+    from . import pipeline
+    if not all(isinstance(t, LazyTransformedView) and t._value is None for t in tviews):
+        return None
+    size = tuple(int(s) for s in stack_properties['size'])
+    for t, p, osp in zip(tviews, params, orig_stack_propertiess):
+        same_frame = (t.shape == size and np.allclose(t.spacing, stack_properties['spacing']) and
+                      np.allclose(t.origin, stack_properties['origin']))
+        same_view = (np.array_equal(t.p, np.asarray(p, dtype=np.float64)) and np.allclose(t.stack.spacing, osp['spacing']) and
+                     np.allclose(t.stack.origin, osp['origin']))
+        if not (same_frame and same_view and t.dtype in (np.dtype(np.uint16), np.dtype(np.float32))):
+            return None
+    if len(tviews) > 8 or len({t.dtype for t in tviews}) != 1:
+        return None
+    dviews = [fusion.to_device(t.stack) for t in tviews]
+    fused = pipeline.fuse_volume_blockwise(dviews, orig_stack_propertiess, params, stack_properties)
+    if tviews[0].dtype != np.uint16:   # the block loop assembles its result in the dtype of the views
+        fused = fused.to(torch.int32).to(torch.float32)
+    return fusion.to_host(fused)
 
 
 def fuse_blockwise_arrays(tviews, params, stack_properties, orig_stack_propertiess, fusion_block_overlap=None,
@@ -413,6 +482,11 @@ def fuse_blockwise_arrays(tviews, params, stack_properties, orig_stack_propertie
     fusion_func = fuse_views_weights if fusion_func is None else fusion_func
     depth = int(fusion_block_overlap or 0)
     chunk = 128
+    if depth == 0 and weights_func == get_weights_simple and fusion_func == fuse_views_weights and not weights_kwargs \
+            and not fusion_kwargs:
+        fused = _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_propertiess)
+        if fused is not None:
+            return fused
     orig_shape = np.array(tviews[0].shape)
     nchunks = [int(-(-s // chunk)) for s in orig_shape]
     weights = None

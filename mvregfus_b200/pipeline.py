@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _cabi, fusion
+from ._host_workers import probe_any_inside_blocks
 
 CHUNK = 128
 
@@ -53,13 +54,11 @@ def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_propertie
         _cabi.check(lib.mvf_chunk_probe(vs.n, vs.structs, probe, _cabi.i32x3(dims), _cabi.i32x3((0, 0, 0)),
                                         C.c_void_p(flags[probe].data_ptr()), chunk, _cabi.i32x3(nch), st))
     # probe-point early-out of get_weights_simple on every 128^3 block (host, float64; mv:3491-3532)
-    probe_ok = np.zeros((int(np.prod(nch)), vs.n), dtype=bool)
     sp = np.asarray(stack_properties["spacing"], dtype=np.float64)
-    for c, loc in enumerate(np.ndindex(*nch)):
-        bprops = {"size": np.array([chunk] * 3), "spacing": sp,
-                  "origin": np.array([stack_properties["origin"][i] + loc[i] * chunk * sp[i] for i in range(3)])}
-        for v in range(vs.n):
-            probe_ok[c, v] = fusion.probe_any_inside(orig_stack_propertiess[v], params[v], bprops, 5)
+    locs = np.array(list(np.ndindex(*nch)), dtype=np.float64)
+    origins = np.asarray(stack_properties["origin"], dtype=np.float64) + locs * chunk * sp
+    probe_ok = np.stack([probe_any_inside_blocks(orig_stack_propertiess[v], params[v], origins, [chunk] * 3, sp, 5)
+                         for v in range(vs.n)], axis=1)
     bits = flags.cpu().numpy().astype(np.uint32)
     info = torch.from_numpy(chunk_decisions(bits[0], bits[1], probe_ok).astype(np.int32)).to(dev)
     if out is None:

@@ -95,13 +95,36 @@ class FftBlur:
 
 def stream_mode():
     """Separable blurs run as two streaming kernels (x/y passes of all planes, then z pass + epilogue) unless
-    MVF_RL_KERNEL selects the fused single-kernel variants (v1: scalar FFMA, v2: FFMA2 plane pairs)."""
-    return os.environ.get("MVF_RL_KERNEL", "v3") not in ("v1", "v2", "1", "2")
+    MVF_RL_KERNEL=v1 selects the fused single-kernel variant (also the fallback for rows that are not 16-byte aligned)."""
+    return os.environ.get("MVF_RL_KERNEL", "v3") not in ("v1", "1")
 
 
 def _vector_aligned(*tensors):
     """16-byte aligned float32 / 8-byte aligned uint16 buffers: what the vector loads of the streaming kernels need."""
     return all(t is None or t.data_ptr() % (16 if t.element_size() == 4 else 8) == 0 for t in tensors)
+
+
+def masked_view(view, weights):
+    """Copy of a view with the voxels zeroed where the weight is <= 1e-5: I = 0 makes the ratio I / (E + 1e-6) exactly 0
+    there, which is all the mask of the reference does (mv:5636, 5695-5699)."""
+    keep = weights > 1e-5
+    if view.dtype == torch.uint16:   # torch.where has no uint16 kernel: same bits as int16
+        return torch.where(keep, view.view(torch.int16), torch.zeros((), dtype=torch.int16, device=view.device)).view(torch.uint16)
+    return torch.where(keep, view, torch.zeros((), dtype=view.dtype, device=view.device))
+
+
+def xy_groups(psf_structs, streamed):
+    """Group index per view: streamed views with identical (ky, kx) factors share the x/y passes of the estimate."""
+    keys, group = [], []
+    for ps, st in zip(psf_structs, streamed):
+        if not st:
+            group.append(-1)
+            continue
+        key = (tuple(ps.ky), tuple(ps.kx), int(ps.ksize[1]), int(ps.ksize[2]))
+        if key not in keys:
+            keys.append(key)
+        group.append(keys.index(key))
+    return group
 
 
 def make_psf_struct(factors):
@@ -178,6 +201,13 @@ class RLPlan:
                          _vector_aligned(vw, ww, self.est, self.ratio, self.corr)
                          for sep, ps, vw, ww in zip(self.separable, self.psf_structs, views, weights)]
         self.tmp = torch.empty(self.dims, dtype=torch.float32, device=dev) if any(self.streamed) else None
+        # streamed views: (1) the mask (w > 1e-5) of the ratio step is burnt into a copy of the view once, so the ratio
+        # pass does not read the weights; (2) views whose PSFs share the in-plane factors (ky, kx) share one x/y pass
+        # of the estimate per iteration
+        self.masked = [masked_view(vw, ww) if st else None for st, vw, ww in zip(self.streamed, views, weights)]
+        self.xy_group, self.xy_tmps = xy_groups(self.psf_structs, self.streamed), []
+        for _ in range(max(self.xy_group) + 1 if any(self.streamed) else 0):
+            self.xy_tmps.append(torch.empty(self.dims, dtype=torch.float32, device=dev))
 
     def init_estimate(self):
         self.sums.zero_()
@@ -189,6 +219,13 @@ class RLPlan:
         """One RL iteration (2 V fused blur kernels); sum(estimate) lands in self.sums[1]."""
         st = _stream_ptr()
         self.sums[1:].zero_()
+        done = set()
+        for v in range(self.n):   # x/y passes of the estimate, once per distinct (ky, kx) pair (the estimate changes only at the end)
+            g = self.xy_group[v]
+            if self.streamed[v] and g not in done:
+                done.add(g)
+                _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est.data_ptr()), self.dims[0], self._dims, C.byref(self.psf_structs[v]),
+                                               C.c_void_p(self.xy_tmps[g].data_ptr()), st))
         for v in range(self.n):
             last = v == self.n - 1
             if self.spectra[v] is not None:  # cuFFT path
@@ -201,9 +238,8 @@ class RLPlan:
             zm = C.c_void_p(self.zmaps[v].data_ptr())
             if self.streamed[v]:  # x/y passes of every plane into tmp, then z pass + epilogue
                 ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp.data_ptr())
-                _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est.data_ptr()), self.dims[0], self._dims, ps, tmp, st))
-                _cabi.check(self.lib.mvf_rl_ratio_z(tmp, zm, self._dims, ps, C.c_void_p(self.views[v].data_ptr()),
-                                                    dtype_code(self.views[v]), C.c_void_p(self.weights[v].data_ptr()),
+                _cabi.check(self.lib.mvf_rl_ratio_z(C.c_void_p(self.xy_tmps[self.xy_group[v]].data_ptr()), zm, self._dims, ps,
+                                                    C.c_void_p(self.masked[v].data_ptr()), dtype_code(self.views[v]), None,
                                                     C.c_void_p(self.ratio.data_ptr()), st))
                 _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.ratio.data_ptr()), self.dims[0], self._dims, ps, tmp, st))
                 _cabi.check(self.lib.mvf_rl_correct_z(tmp, zm, self._dims, ps, C.c_void_p(self.weights[v].data_ptr()),
@@ -318,6 +354,11 @@ class SlabRLPlan:
                          _vector_aligned(vw, ww, self.est, self.ratio, self.corr)
                          for sp, ps, vw, ww in zip(self.spectra, self.psf_structs, views, weights)]
         self.tmp_pad = torch.empty_like(self.est_pad) if any(self.streamed) else None
+        # as in RLPlan: mask burnt into a copy of the streamed views, one x/y pass of the estimate per (ky, kx) pair
+        self.masked = [masked_view(vw, ww) if st else None for st, vw, ww in zip(self.streamed, views, weights)]
+        self.xy_group, self.xy_tmps = xy_groups(self.psf_structs, self.streamed), []
+        for _ in range(max(self.xy_group) + 1 if any(self.streamed) else 0):
+            self.xy_tmps.append(torch.empty_like(self.est_pad))
 
     def init_estimate(self):
         self.sums.zero_()
@@ -325,17 +366,18 @@ class SlabRLPlan:
                                                   C.c_void_p(self.est.data_ptr()), self.est.numel(),
                                                   C.c_void_p(self.sums.data_ptr()), _stream_ptr()))
 
-    def _xy_planes(self, src_pad, v, pending=()):
-        """x/y passes of src_pad into tmp_pad.  With a halo exchange in flight (`pending`) the own planes go first
-        and the halo planes follow once they have arrived, so the transfer runs beside the bulk of the work."""
+    def _xy_planes(self, src_pad, v, pending=(), dst=None):
+        """x/y passes of src_pad into dst (default tmp_pad).  With a halo exchange in flight (`pending`) the own planes
+        go first and the halo planes follow once they have arrived, so the transfer runs beside the bulk of the work."""
         from . import slab
         ps, st = C.byref(self.psf_structs[v]), _stream_ptr()
         nzl, rp = self.dims[0], self.rp
         pstride = self.dims[1] * self.dims[2] * 4
+        dst = self.tmp_pad if dst is None else dst
 
         def run(p0, n):
             _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(src_pad.data_ptr() + p0 * pstride), int(n), self._dims, ps,
-                                           C.c_void_p(self.tmp_pad.data_ptr() + p0 * pstride), st))
+                                           C.c_void_p(dst.data_ptr() + p0 * pstride), st))
         if not pending or rp == 0:
             slab.exchange_halos_end(pending)
             run(0, nzl + 2 * rp)
@@ -354,19 +396,30 @@ class SlabRLPlan:
             self.fft.blur(self.est_pad, self.zmap, self.rp, self.spectra[v], 1, view=self.views[v],
                           weights=self.weights[v], out=self.ratio)
             return
-        if self.streamed[v]:
-            ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp_pad.data_ptr())
-            self._xy_planes(self.est_pad, v, pending)
-            _cabi.check(self.lib.mvf_rl_ratio_z(tmp, C.c_void_p(self.zmap.data_ptr()), self._dims, ps,
-                                                C.c_void_p(self.views[v].data_ptr()), dtype_code(self.views[v]),
-                                                C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.ratio.data_ptr()),
-                                                _stream_ptr()))
+        if self.streamed[v]:   # the x/y passes of the estimate were done once per (ky, kx) group (xy_estimate)
+            slab.exchange_halos_end(pending)
+            _cabi.check(self.lib.mvf_rl_ratio_z(C.c_void_p(self.xy_tmps[self.xy_group[v]].data_ptr()),
+                                                C.c_void_p(self.zmap.data_ptr()), self._dims, C.byref(self.psf_structs[v]),
+                                                C.c_void_p(self.masked[v].data_ptr()), dtype_code(self.views[v]), None,
+                                                C.c_void_p(self.ratio.data_ptr()), _stream_ptr()))
             return
         slab.exchange_halos_end(pending)
         _cabi.check(self.lib.mvf_rl_ratio(C.c_void_p(self.est_pad.data_ptr()), C.c_void_p(self.zmap.data_ptr()), self._dims,
                                           C.byref(self.psf_structs[v]), C.c_void_p(self.views[v].data_ptr()),
                                           dtype_code(self.views[v]), C.c_void_p(self.weights[v].data_ptr()),
                                           C.c_void_p(self.ratio.data_ptr()), _stream_ptr()))
+
+    def xy_estimate(self, pending=()):
+        """x/y passes of the halo-padded estimate, once per group of streamed views with equal in-plane PSF factors;
+        returns the requests that are still pending (none once a group has consumed the halos)."""
+        done = set()
+        for v in range(self.n):
+            g = self.xy_group[v]
+            if self.streamed[v] and g not in done:
+                done.add(g)
+                self._xy_planes(self.est_pad, v, pending, dst=self.xy_tmps[g])
+                pending = ()
+        return pending
 
     def step_correct(self, v, pending=()):
         """C (+)= blur(R_v) * w_v; the last view applies the multiplicative update to the estimate (`pending`:
@@ -399,6 +452,7 @@ class SlabRLPlan:
         self.sums[1:].zero_()
         # one estimate exchange serves all views' first blur; every exchange runs beside the x/y passes of the own planes
         pending = slab.exchange_halos_begin(self.est_pad, self.halo, self.group)
+        pending = self.xy_estimate(pending)
         for v in range(self.n):
             self.step_ratio(v, pending)
             pending = slab.exchange_halos_begin(self.ratio_pad, self.halo, self.group)

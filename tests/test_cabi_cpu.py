@@ -125,3 +125,22 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_block_probe_matches_per_block_probe():
+    """The all-blocks-at-once probe of the device pipeline decides exactly like the per-block probe loop
+    (get_weights_simple's early-out, mv:3491-3532), jittered and exactly aligned geometries alike."""
+    from mvregfus_b200 import synthetic
+    from mvregfus_b200._host_workers import probe_any_inside_blocks, probe_flags
+    shape = (100, 90, 140)
+    for jitter in (True, False):
+        params = synthetic.view_params(shape, 4, seed=11, jitter=jitter)
+        props = {"size": np.array(shape), "spacing": np.array([1.0, 0.5, 0.5]), "origin": np.array([0.0, -3.0, 2.0])}
+        sp = np.array([1.0, 1.0, 1.0])
+        locs = np.array(list(np.ndindex(3, 3, 4)), dtype=np.float64)
+        origins = np.array([-64.0, -128.0, 0.0]) + locs * 64 * sp
+        for p in params:
+            fast = probe_any_inside_blocks(props, p, origins, [64] * 3, sp, 5)
+            slow = np.array([probe_flags(props, p, {"size": np.array([64] * 3), "spacing": sp, "origin": o}, 5).any()
+                             for o in origins])
+            assert np.array_equal(fast, slow)

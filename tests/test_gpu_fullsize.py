@@ -90,6 +90,8 @@ def test_rl_full_size_slab_consistency(cuda):
         p.init_estimate()
     for _ in range(2):
         slab.exchange_halos_local([p.est_pad for p in plans], [p.halo for p in plans])
+        for p in plans:
+            p.xy_estimate()
         for v in range(V):
             for p in plans:
                 p.step_ratio(v)
