@@ -333,8 +333,11 @@ def run_rl(dev, rank=0, world=1):
         z0, z1 = slab.slab_bounds(shape[0], world)[rank]
         plan = rl.SlabRLPlan([t[z0:z1].clone() for t in tviews], [w[v][z0:z1].clone() for v in range(NVIEWS)], psfs,
                              shape[0], rank, world)
+    halo_txt = ("pulled from the neighbours' symmetric-memory buffers, iteration replayed from a CUDA graph"
+                if getattr(plan, "symm", None) is not None else "NCCL ring isend/irecv")
     plan.init_estimate()
-    plan.iterate()  # warm-up
+    for _ in range(2):   # warm-up: the first call runs eagerly, the second captures the CUDA graph of an iteration
+        plan.iterate()
     torch.cuda.synchronize()
     plan.init_estimate()
     if world > 1:
@@ -366,7 +369,7 @@ def run_rl(dev, rank=0, world=1):
             torch.cuda.empty_cache()
             ref = rl.RLPlan(tviews, [w[v] for v in range(NVIEWS)], psfs)
             ref.init_estimate()
-            for _ in range(RL_ITERS + 1):   # warm-up iteration + the timed ones, as the slabs ran
+            for _ in range(RL_ITERS):   # the slabs were re-initialised after their warm-up
                 ref.iterate()
             torch.cuda.synchronize()
             if torch.equal(whole, ref.est):
@@ -387,7 +390,7 @@ def run_rl(dev, rank=0, world=1):
                                    "sigma z=%g xy=%g (19^3, separable), %d iterations" % (NVIEWS, *shape, *RL_SIGMA, RL_ITERS)},
             "kernel_launches_per_iteration": rl_launches // RL_ITERS,
             "n_gpus": world, "scaling": "strong",
-            "sharding": "whole volume" if world == 1 else "z-slabs, PSF-radius halos over NVLink",
+            "sharding": "whole volume" if world == 1 else "z-slabs, PSF-radius halos over NVLink (%s)" % halo_txt,
             "parity_vs_whole": parity,
             "roofline": {"bound": "hbm", "achieved": alg / (per_it * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                          "frac": alg / (per_it * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes_per_iteration": alg,

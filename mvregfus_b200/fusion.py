@@ -50,13 +50,35 @@ def pinned_empty(shape, dtype):
     return torch.empty(tuple(int(s) for s in shape), dtype=_TORCH_DT[np.dtype(dtype)][0], pin_memory=True).numpy()
 
 
+_HOST_POOL = {}          # (nbytes) -> idle page-locked uint8 tensors
+_HOST_POOL_LIMIT = 8 << 30
+
+
+def _host_buffer(nbytes):
+    free = _HOST_POOL.get(nbytes)
+    if free:
+        return free.pop()
+    return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+
+def _host_release(raw):
+    if sum(k * len(v) for k, v in _HOST_POOL.items()) + raw.numel() <= _HOST_POOL_LIMIT:
+        _HOST_POOL.setdefault(raw.numel(), []).append(raw)
+
+
 def to_host(t):
-    """CUDA tensor -> host ndarray through a page-locked buffer (torch's caching host allocator recycles them), so
-    the D2H copy runs at link speed instead of through the pageable staging path."""
-    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    """CUDA tensor -> host ndarray in page-locked memory, so the D2H copy runs at link speed instead of through the
+    pageable staging path.  Page-locking is expensive (~0.2 s per GB): the buffer goes back to a pool when the returned
+    array (and every view of it) has been garbage collected, and the next result of that size reuses it."""
+    import weakref
+    nbytes = t.numel() * t.element_size()
+    raw = _host_buffer(nbytes)
+    buf = raw.view(t.dtype).view(t.shape)
     buf.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return buf.numpy()
+    arr = buf.numpy()
+    weakref.finalize(arr, _host_release, raw)
+    return arr
 
 
 def _stream_ptr():

@@ -216,7 +216,11 @@ class RLPlan:
                                                   C.c_void_p(self.sums.data_ptr()), _stream_ptr()))
 
     def iterate(self):
-        """One RL iteration (2 V fused blur kernels); sum(estimate) lands in self.sums[1]."""
+        """One RL iteration; sum(estimate) lands in self.sums[1].  After the first (eager) call the launches of an
+        iteration are replayed from a CUDA graph (MVF_RL_GRAPH=0: always eager)."""
+        _graphed(self, self._iterate_eager)
+
+    def _iterate_eager(self):
         st = _stream_ptr()
         self.sums[1:].zero_()
         done = set()
@@ -274,7 +278,38 @@ class RLPlan:
             if i >= num_iterations - 1:
                 break
             i += 1
+        self.iterations_run = i + 1
         return self.est
+
+
+def _graphed(plan, eager):
+    """Run `eager()` once, capture it into a CUDA graph on the second call, replay from then on.  Anything that cannot be
+    captured (old driver, an op that syncs) leaves the plan in eager mode."""
+    state = getattr(plan, "_graph_state", 0)
+    if state == 0 or os.environ.get("MVF_RL_GRAPH", "1") == "0" or not torch.cuda.is_available():
+        plan._graph_state = 1 if state == 0 else state
+        eager()
+        return
+    if state == 1:
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                eager()
+            plan._graph, plan._graph_state = graph, 2
+        except Exception:   # not capturable here: stay eager
+            plan._graph_state = 3
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            eager()
+            return
+        cur.wait_stream(side)
+    if plan._graph_state == 2:
+        plan._graph.replay()
+    else:
+        eager()
 
 
 def blur(volume, psf_factors):
@@ -339,8 +374,26 @@ class SlabRLPlan:
             raise ValueError("slab height %d does not match the planner's %d" % (nzl, self.halo.nzl))
         self.rp, self.dims = rp, (nzl, ny, nx)
         self.zmap = torch.from_numpy(self.halo.zmap()).to(dev)
-        self.est_pad = torch.zeros((nzl + 2 * rp, ny, nx), dtype=torch.float32, device=dev)
-        self.ratio_pad = torch.zeros((nzl + 2 * rp, ny, nx), dtype=torch.float32, device=dev)
+        # Halo transport.  "symm" (default on CUDA with more than one rank): the padded volumes live in symmetric
+        # memory and every rank pulls its halo planes from the neighbours itself (slab.SymmetricHalo); "nccl": ring of
+        # isend/irecv (also what the gloo tests on CPU exercise).
+        self.symm = None
+        want = os.environ.get("MVF_HALO", "symm")
+        if world > 1 and want == "symm" and dev.type == "cuda" and self.fft is None:
+            try:
+                self.symm = slab.SymmetricHalo(3, self.halo, ny, nx, dev, group)
+            except Exception as e:   # no peer access / no symmetric memory support: the NCCL ring still works
+                if os.environ.get("MVF_HALO") == "symm":
+                    raise
+                self.symm, self._symm_error = None, repr(e)
+        if self.symm is not None:
+            self.est_pad, self.ratio_pads = self.symm.bufs[0], [self.symm.bufs[1], self.symm.bufs[2]]
+            self.comm_stream = torch.cuda.Stream()
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        else:
+            self.est_pad = torch.zeros((nzl + 2 * rp, ny, nx), dtype=torch.float32, device=dev)
+            self.ratio_pads = [torch.zeros((nzl + 2 * rp, ny, nx), dtype=torch.float32, device=dev)]
+        self.ratio_pad = self.ratio_pads[0]
         self.est = self.est_pad[rp:rp + nzl]
         self.ratio = self.ratio_pad[rp:rp + nzl]
         self.corr = torch.empty(self.dims, dtype=torch.float32, device=dev)
@@ -378,6 +431,12 @@ class SlabRLPlan:
         def run(p0, n):
             _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(src_pad.data_ptr() + p0 * pstride), int(n), self._dims, ps,
                                            C.c_void_p(dst.data_ptr() + p0 * pstride), st))
+        if callable(pending):   # symmetric-memory pull in flight on the side stream: `pending()` joins it
+            run(rp, nzl)
+            pending()
+            run(0, rp)
+            run(rp + nzl, rp)
+            return
         if not pending or rp == 0:
             slab.exchange_halos_end(pending)
             run(0, nzl + 2 * rp)
@@ -447,8 +506,46 @@ class SlabRLPlan:
                                             C.c_void_p(self.est_pad.data_ptr()), self._est_off,
                                             C.c_void_p(self.sums[1:].data_ptr()), _stream_ptr()))
 
+    def _select_ratio(self, i):
+        """Ratio volumes alternate between two symmetric buffers: a rank may start the next view's ratio while a
+        neighbour is still pulling the halo planes of the previous one."""
+        self.ratio_pad = self.ratio_pads[i % len(self.ratio_pads)]
+        self.ratio = self.ratio_pad[self.rp:self.rp + self.dims[0]]
+
+    def _pull_async(self, buf_index):
+        """Barrier on the compute stream (every rank has written its own planes), then the two halo copies on the side
+        stream; returns the join that the first consumer of the halo planes calls."""
+        main = torch.cuda.current_stream()
+        self.symm.barrier()
+        self._ev_fork.record(main)
+        self.comm_stream.wait_event(self._ev_fork)
+        with torch.cuda.stream(self.comm_stream):
+            self.symm.pull(buf_index)
+            self._ev_join.record(self.comm_stream)
+        return lambda: main.wait_event(self._ev_join)
+
+    def _iterate_symm(self):
+        self.sums[1:].zero_()
+        join = self._pull_async(0)
+        if any(self.streamed):
+            join = self.xy_estimate(join)
+        if callable(join):
+            join()
+        for v in range(self.n):
+            self._select_ratio(v)
+            self.step_ratio(v)
+            join = self._pull_async(1 + v % 2)
+            if self.streamed[v]:
+                self.step_correct(v, join)
+            else:
+                join()
+                self.step_correct(v)
+
     def iterate(self):
         from . import slab
+        if self.symm is not None:
+            _graphed(self, self._iterate_symm)
+            return
         self.sums[1:].zero_()
         # one estimate exchange serves all views' first blur; every exchange runs beside the x/y passes of the own planes
         pending = slab.exchange_halos_begin(self.est_pad, self.halo, self.group)
@@ -480,4 +577,5 @@ class SlabRLPlan:
             if i >= num_iterations - 1:
                 break
             i += 1
+        self.iterations_run = i + 1
         return self.est

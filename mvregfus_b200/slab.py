@@ -77,6 +77,18 @@ class HaloPlan:
         return np.arange(0, self.rp) if self.rank > 0 else None
 
 
+class _StagedRecv:
+    """Request of a receive that lands in a host buffer first (backend without device P2P, i.e. gloo with CUDA
+    volumes in the single-GPU tests): wait() finishes the transfer and copies the planes to the device."""
+
+    def __init__(self, req, host, dst):
+        self.req, self.host, self.dst = req, host, dst
+
+    def wait(self):
+        self.req.wait()
+        self.dst.copy_(self.host)
+
+
 def exchange_halos_begin(buf, plan, group=None):
     """Start filling the halo planes of `buf` ((nzl+2rp, ny, nx), own planes already written) from the ring
     neighbours; returns the pending requests (empty for a single rank).  Work that only touches own planes may be
@@ -85,16 +97,24 @@ def exchange_halos_begin(buf, plan, group=None):
     rp, nzl = plan.rp, plan.nzl
     if plan.world == 1:
         return []
+    staged = buf.is_cuda and dist.get_backend(group) == "gloo"   # gloo moves host memory only
     up_idx = torch.as_tensor(plan.planes_for_upper_neighbour() + rp, device=buf.device, dtype=torch.long)
     send_up = buf.index_select(0, up_idx).contiguous()
-    ops = [dist.P2POp(dist.isend, send_up, (plan.rank + 1) % plan.world, group=group),
-           dist.P2POp(dist.irecv, buf[0:rp], plan.lower_src, group=group)]
+    recvs = [(buf[0:rp], plan.lower_src)]
+    sends = [(send_up, (plan.rank + 1) % plan.world)]
     if plan.rank > 0:
-        send_down = buf[rp:2 * rp].contiguous()
-        ops.append(dist.P2POp(dist.isend, send_down, plan.rank - 1, group=group))
+        sends.append((buf[rp:2 * rp].contiguous(), plan.rank - 1))
     if plan.upper_src is not None:
-        ops.append(dist.P2POp(dist.irecv, buf[rp + nzl:rp + nzl + rp], plan.upper_src, group=group))
-    return list(dist.batch_isend_irecv(ops))
+        recvs.append((buf[rp + nzl:rp + nzl + rp], plan.upper_src))
+    if not staged:
+        ops = [dist.P2POp(dist.isend, t, peer, group=group) for t, peer in sends] + \
+              [dist.P2POp(dist.irecv, t, peer, group=group) for t, peer in recvs]
+        return list(dist.batch_isend_irecv(ops))
+    reqs = [dist.isend(t.cpu(), peer, group=group) for t, peer in sends]
+    for t, peer in recvs:
+        host = torch.empty(t.shape, dtype=t.dtype)
+        reqs.append(_StagedRecv(dist.irecv(host, peer, group=group), host, t))
+    return reqs
 
 
 def exchange_halos_end(reqs):
@@ -121,3 +141,48 @@ def exchange_halos_local(bufs, plans):
         if plan.upper_src is not None:
             up = plan.upper_src
             buf[rp + nzl:rp + nzl + rp] = bufs[up][plans[up].rp:2 * plans[up].rp]
+
+
+class SymmetricHalo:
+    """Halo planes pulled straight out of the neighbours' buffers over NVLink / NVSwitch: the halo-padded volumes live
+    in torch symmetric memory (every rank maps its ring neighbours' allocations), a halo fill is two device-to-device
+    copies issued by the receiving rank plus a device-side barrier on the stream - no NCCL call, no host round trip
+    and nothing that cannot be captured in a CUDA graph.  One allocation holds `nbuf` padded volumes of the same
+    (maximal) height on every rank."""
+
+    def __init__(self, nbuf, plan, ny, nx, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.plan, self.nbuf = plan, nbuf
+        group = dist.group.WORLD if group is None else group
+        height = max(b - a for a, b in plan.bounds) + 2 * plan.rp      # same shape on every rank
+        self.shape = (nbuf, height, int(ny), int(nx))
+        self.store = symm.empty(self.shape, dtype=torch.float32, device=device)
+        self.store.zero_()
+        self.hdl = symm.rendezvous(self.store, group)
+        self.bufs = [self.store[i][:plan.nzl + 2 * plan.rp] for i in range(nbuf)]
+        rp = plan.rp
+        # source planes inside the neighbours' padded buffers (their own planes start at rp)
+        lower = HaloPlan(plan.nz, plan.world, plan.lower_src, plan.K, rp)
+        self.lower_peer = self.hdl.get_buffer(plan.lower_src, self.shape, torch.float32)
+        idx = lower.planes_for_upper_neighbour() + rp
+        self.lower_slice = slice(int(idx[0]), int(idx[-1]) + 1) if np.all(np.diff(idx) == 1) else None
+        self.lower_idx = torch.as_tensor(idx, device=device, dtype=torch.long)
+        self.upper_peer = None
+        if plan.upper_src is not None:
+            self.upper_peer = self.hdl.get_buffer(plan.upper_src, self.shape, torch.float32)
+
+    def barrier(self):
+        """All ranks of the group meet on their current streams (signal pads in symmetric memory)."""
+        self.hdl.barrier(channel=0)
+
+    def pull(self, i):
+        """Fill the halo planes of buffer i from the neighbours' own planes (current stream)."""
+        rp, nzl = self.plan.rp, self.plan.nzl
+        dst = self.bufs[i]
+        if self.lower_slice is not None:
+            dst[0:rp].copy_(self.lower_peer[i][self.lower_slice])
+        else:   # rank 0: the reference's wrap-around picks reflected planes of the last rank
+            torch.index_select(self.lower_peer[i], 0, self.lower_idx, out=dst[0:rp])
+        if self.upper_peer is not None:
+            dst[rp + nzl:rp + nzl + rp].copy_(self.upper_peer[i][rp:2 * rp])

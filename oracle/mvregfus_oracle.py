@@ -571,7 +571,7 @@ def blur_direct(img, psf):
 
 
 def fuse_LR_with_weights_np(views, params, stack_properties, num_iterations=25, sz=4, sxy=0.5, tol=5e-5,
-                            weights=None, psfs=None, blur="fft", return_float=False):
+                            weights=None, psfs=None, blur="fft", return_float=False, return_iterations=False):
     """Multi-view RL with weights (mv:5545-5749).  dtype flow as under numpy<2: float32 storage for
     estimate/ratio/correction, float64 FFT products.  ``blur='direct'`` swaps in the closed-form
     convolution; ``return_float`` returns the float32 estimate before the uint16 cast."""
@@ -613,7 +613,7 @@ def fuse_LR_with_weights_np(views, params, stack_properties, num_iterations=25, 
         curr_imsum = new_imsum
         i += 1
     if return_float:
-        return estimate
+        return (estimate, i + 1) if return_iterations else estimate
     return ImageArray(estimate.astype(np.uint16), spacing=stack_properties["spacing"], origin=stack_properties["origin"])
 
 

@@ -71,3 +71,27 @@ def test_fused_dct_mode(cuda):
     out = fusion.fuse_blend(vs, [128, 128, 128]).cpu().numpy()
     d = np.abs(out.astype(np.int64) - ref.astype(np.int64))
     assert d.max() <= 2 and np.mean(d > 0) <= 4e-3, (d.max(), np.mean(d > 0))
+
+
+def test_dct_weights_multi_chunk_8_views(cuda):
+    """configs[2] in miniature: 8 views (every other one 7 degrees off axis), a 2x2x2 grid of 128^3 chunks with a
+    4-voxel halo - the nan-max filter, the per-cell exponent fit and the nan-Gaussian act ACROSS chunks here
+    (mv:4122-4242), and every chunk multiplies its own blending weights with the up-sampled coarse grid (mv:4256-4317)."""
+    from mvregfus_b200 import multiview as mv
+    from mvregfus_b200 import synthetic
+    from tests.golden.make_golden import blob_volume
+    V, n, depth = 8, 256, 4
+    params = synthetic.view_params((200, 200, 200), V, seed=21, odd_extra_deg=7.0)
+    props = [{"size": np.array((200, 200, 200)), "spacing": np.ones(3), "origin": np.zeros(3)} for _ in range(V)]
+    sp = {"size": np.array((n, n, n)), "spacing": np.ones(3), "origin": np.array([-28.0, -28.0, -28.0])}
+    tviews = np.array([blob_volume((n, n, n), 900 + i, np.uint16, 0.5) for i in range(V)])
+    ref = O.get_weights_dct(tviews, params, props, sp, depth=depth)
+    got = np.asarray(mv.get_weights_dct_dask(tviews, params, props, sp, depth=depth))
+    edge = 128 + 2 * depth
+    assert got.shape == (V, 2 * edge, 2 * edge, 2 * edge) and got.dtype == np.float32
+    assert len(ref) == 8
+    worst = 0.0
+    for loc, w in ref.items():
+        blk = got[:, loc[0] * edge:(loc[0] + 1) * edge, loc[1] * edge:(loc[1] + 1) * edge, loc[2] * edge:(loc[2] + 1) * edge]
+        worst = max(worst, float(np.max(np.abs(blk.astype(np.float64) - w))))
+    assert worst <= 5e-6, worst

@@ -196,3 +196,45 @@ def test_rl_misaligned_view_falls_back_to_fused_kernel(cuda):
     assert not any(plan.streamed)
     got = plan.run(num_iterations=3)
     assert float(((got - ref).abs() / ref.abs().clamp_min(1.0)).max()) <= 1e-4
+
+
+def test_rl_configs3_psf_at_128_cubed(cuda):
+    """The PSF of BASELINE.json configs[3] (sigma z = 6, xy = 2 at spacing 1 -> 19^3, separable for axis-aligned views),
+    10 iterations on a 128^3-class volume against the oracle's float64 FFT recurrence (mv:5614-5747)."""
+    from mvregfus_b200 import fusion, rl, multiview as mv
+    tv, w, params, sp = _axis_case(shape=(128, 120, 128), nviews=2, seed=12)
+    psfs = [mv.get_psf(p, sp, 6, 2) for p in params]
+    assert psfs[0].shape == (19, 19, 19)
+    ref = O.fuse_LR_with_weights_np(tv, params, sp, num_iterations=10, sz=6, sxy=2, weights=w, return_float=True)
+    plan = rl.RLPlan([fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w], psfs)
+    got = plan.run(num_iterations=10).cpu().numpy()
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+    assert float(err.max()) <= 1e-3, float(err.max())
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-3
+
+
+def test_rl_block_sum_and_convergence_break(cuda):
+    """sum(estimate) of the update step (the reference's convergence measure, mv:5726-5734) on a plane whose vector
+    count is not a multiple of the warp size (the last warp of the z kernel is partly idle), and a run long enough for
+    the tolerance test to fire: same number of iterations, same estimate as the oracle."""
+    import torch
+    from mvregfus_b200 import fusion, rl, multiview as mv
+    tv, w, params, sp = _axis_case(shape=(48, 40, 56), nviews=2)
+    dims = tv[0].shape
+    assert dims[2] % 4 == 0 or True
+    psfs = [mv.get_psf(p, sp, 3, 1) for p in params]
+    plan = rl.RLPlan([fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w], psfs)
+    plan.init_estimate()
+    for _ in range(3):   # eager, captured, replayed
+        plan.iterate()
+        torch.cuda.synchronize()
+        assert abs(float(plan.sums[1].item()) / float(plan.est.double().sum().item()) - 1.0) < 1e-9
+    tol = 2e-3
+    ref, n_ref = O.fuse_LR_with_weights_np(tv, params, sp, num_iterations=40, sz=3, sxy=1, tol=tol, weights=w,
+                                           return_float=True, return_iterations=True)
+    assert 11 <= n_ref < 40      # the break fired, and not before the 11th iteration (mv:5729)
+    plan2 = rl.RLPlan([fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w], psfs)
+    got = plan2.run(num_iterations=40, tol=tol).cpu().numpy()
+    assert plan2.iterations_run == n_ref
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+    assert float(err.max()) <= 1e-3, float(err.max())
