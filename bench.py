@@ -336,22 +336,23 @@ def run_rl(dev, rank=0, world=1):
     halo_txt = ("pulled from the neighbours' symmetric-memory buffers, iteration replayed from a CUDA graph"
                 if getattr(plan, "symm", None) is not None else "NCCL ring isend/irecv")
     plan.init_estimate()
-    for _ in range(2):   # warm-up: the first call runs eagerly, the second captures the CUDA graph of an iteration
-        plan.iterate()
+    _cabi.launch_count(reset=True)
+    plan.iterate()       # warm-up 1 runs eagerly (its launches are counted), warm-up 2 captures the CUDA graph of an iteration
+    launches_per_iteration = _cabi.launch_count()
+    plan.iterate()
     torch.cuda.synchronize()
     plan.init_estimate()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    _cabi.launch_count(reset=True)
     a.record()
     for _ in range(RL_ITERS):
         plan.iterate()
     b.record()
     torch.cuda.synchronize()
-    rl_launches = _cabi.launch_count()
     ms = a.elapsed_time(b)
+    graphed = getattr(plan, "_graph_state", 0) == 2   # the timed iterations were replays of a captured CUDA graph
     parity = None
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -388,7 +389,8 @@ def run_rl(dev, rank=0, world=1):
     return {"metric": "rl_iterations_per_s", "value": 1e3 / per_it, "unit": "it/s", "ms_per_iteration": per_it,
             "config": {"workload": "BASELINE.json configs[3]: %d views %dx%dx%d uint16 in the fused frame, Gaussian PSF "
                                    "sigma z=%g xy=%g (19^3, separable), %d iterations" % (NVIEWS, *shape, *RL_SIGMA, RL_ITERS)},
-            "kernel_launches_per_iteration": rl_launches // RL_ITERS,
+            "kernel_launches_per_iteration": launches_per_iteration,
+            "cuda_graph": graphed,
             "n_gpus": world, "scaling": "strong",
             "sharding": "whole volume" if world == 1 else "z-slabs, PSF-radius halos over NVLink (%s)" % halo_txt,
             "parity_vs_whole": parity,
@@ -593,6 +595,19 @@ def run_b200(args):
         rl_obj = run_rl(dev, rank, world)
         if rank == 0:
             line["rl"] = rl_obj
+    if world >= 2 and not args.skip_extra:   # the multi-GPU configurations of BASELINE.json, one z-slab per rank
+        from tools import extra_configs
+        torch.cuda.empty_cache()
+        xviews, xparams, xprops = extra_configs.make_views(dev)
+        c2 = extra_configs.config2(dev, rank, world, xviews, xparams, xprops)
+        if rank == 0:
+            line["configs2"] = c2
+        if world == 8:
+            c4 = extra_configs.config4(dev, rank, world, 10, xviews, xparams, xprops)
+            if rank == 0:
+                line["configs4"] = c4
+        del xviews
+        torch.cuda.empty_cache()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             box = 256
@@ -612,6 +627,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-rl", action="store_true")
+    ap.add_argument("--skip-extra", action="store_true", help="no configs[2] / configs[4] extra keys at N >= 2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
