@@ -20,10 +20,9 @@ def probe_flags(orig_props, p, stack_properties, n_points):
     return flags
 
 
-def probe_any_inside_blocks(orig_props, p, origins, size, spacing, n_points):
-    """`probe_flags(...).any()` for many target boxes of one size at once (origins: (B, 3) physical corners): the
-    probe-point early-out of get_weights_simple (mv:3491-3532) for every 128^3 block of a volume.  Same arithmetic per
-    point, evaluated column-wise on all points of all boxes."""
+def probe_inside_blocks(orig_props, p, origins, size, spacing, n_points):
+    """probe_flags for many target boxes of one size at once (origins: (B, 3) physical corners) -> bool (B, n^3).  Same
+    arithmetic per point as the per-box loop, evaluated column-wise on all points of all boxes."""
     rel = np.linspace(0, 1, n_points)
     grid = np.stack(np.meshgrid(rel, rel, rel, indexing="ij"), -1).reshape(-1, 3)              # (P, 3)
     origins = np.asarray(origins, dtype=np.float64)
@@ -36,7 +35,22 @@ def probe_any_inside_blocks(orig_props, p, origins, size, spacing, n_points):
         y = A[d, 0] * phys[..., 0] + A[d, 1] * phys[..., 1] + A[d, 2] * phys[..., 2]
         pix = (y + c[d] - orig_props["origin"][d]) / orig_props["spacing"][d]
         inside &= (pix >= 0) & (pix < vsize[d])
-    return inside.any(axis=1)
+    return inside
+
+
+def probe_any_inside_blocks(orig_props, p, origins, size, spacing, n_points):
+    """The probe-point early-out of get_weights_simple (mv:3491-3532) for every block of a volume: True where any of
+    the n^3 probe points of the block falls inside the view."""
+    return probe_inside_blocks(orig_props, p, origins, size, spacing, n_points).any(axis=1)
+
+
+def block_codes_all(orig_stack_propertiess, params, origins, size, spacing, n_points=2):
+    """blocks_inside codes (1 all probe points inside / 2 some / 0 none, mv:3406-3466) of many boxes -> int64 (B, V)."""
+    codes = np.zeros((len(origins), len(params)), dtype=np.int64)
+    for v, (osp, p) in enumerate(zip(orig_stack_propertiess, params)):
+        f = probe_inside_blocks(osp, p, origins, size, spacing, n_points)
+        codes[:, v] = np.where(f.all(axis=1), 1, np.where(f.any(axis=1), 2, 0))
+    return codes
 
 
 def blocks_inside_codes(orig_stack_propertiess, params, stack_properties, n_points_per_dim=5):

@@ -1,9 +1,9 @@
 """Optional worker processes for the embarrassingly parallel host loops of the DCT-weight path (per-block view probes,
 per-cell L-BFGS-B exponent fits: 1.2 s + 2.8 s of single-threaded Python for 8 views on a 512x1024x1024 frame).
 
-Opt-in: ``MVF_HOST_WORKERS=N`` (N >= 2) starts N plain subprocesses ``python -m mvregfus_b200._host_workers`` that
+``MVF_HOST_WORKERS=N`` (N >= 2; default: this rank's share of the host cores minus one, at most 16) starts N plain subprocesses ``python -m mvregfus_b200._host_workers`` that
 import numpy/scipy only (no torch, nothing of the caller's process is forked or re-imported) and exchange
-length-prefixed pickles over pipes.  Default (unset, 0 or 1): the loops run serially in this process.  Any worker
+length-prefixed pickles over pipes.  With 0 or 1 the loops run serially in this process.  Any worker
 failure or timeout kills the workers and reruns the tasks serially - per item the code is the same function, so the
 results are identical bit for bit either way."""
 import atexit
@@ -18,10 +18,17 @@ _procs = []
 
 
 def workers():
+    """MVF_HOST_WORKERS=N; unset: the host cores of this rank (cores / ranks on the node, at most 16) minus one."""
     try:
-        return max(0, int(os.environ.get("MVF_HOST_WORKERS", "0")))
-    except ValueError:
-        return 0
+        return max(0, int(os.environ["MVF_HOST_WORKERS"]))
+    except (KeyError, ValueError):
+        pass
+    try:
+        share = len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except (AttributeError, ValueError):
+        share = 1
+    n = min(16, share - 1)
+    return n if n >= 2 else 0
 
 
 def shutdown():

@@ -85,14 +85,12 @@ def quality_grid(tviews, params, orig_stack_propertiess, stack_properties):
     nv = len(tviews)
     qspacing = spacing * b
     # which views see which block (2^3 probe points, bit-exact host arithmetic)
-    inside = np.zeros((nv,) + tuple(nb), dtype=np.int64)
-    locs = list(np.ndindex(*nb))
+    locs = np.array(list(np.ndindex(*nb)), dtype=np.int64)
     props_np = [{k: np.asarray(v) for k, v in osp.items()} for osp in orig_stack_propertiess]
-    tasks = [(locs[a:b2], np.asarray(stack_properties["origin"], dtype=np.float64), size, np.array(qspacing), props_np,
-              np.asarray(params, dtype=np.float64)) for a, b2 in _hostpool.chunks(len(locs))]
-    codes = np.concatenate(_hostpool.pmap(_host_workers.block_codes_chunk, tasks, min_tasks=2 if len(locs) >= 256 else 10 ** 9))
-    for n, loc in enumerate(locs):
-        inside[(slice(None),) + loc] = codes[n]
+    origins = np.asarray(stack_properties["origin"], dtype=np.float64) + locs * size * np.array(qspacing)
+    codes = _host_workers.block_codes_all(props_np, np.asarray(params, dtype=np.float64), origins,
+                                          np.array([size] * 3).astype(np.int64), np.array(qspacing), 2)
+    inside = np.ascontiguousarray(codes.T).reshape((nv,) + tuple(nb))
     seen = inside > 0
     nseen = seen.sum(0)
     ws = np.full((nv,) + tuple(nb), np.nan, dtype=np.float64)

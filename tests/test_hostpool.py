@@ -54,3 +54,20 @@ def test_dead_workers_fall_back_to_serial(monkeypatch):
     finally:
         _hostpool.shutdown()
     assert np.array_equal(out, _host_workers.adapt_cells_chunk((cells, 2, 0.9)))
+
+
+def test_block_codes_all_equals_per_block_loop():
+    """The all-blocks-at-once view probe of the DCT quality grid gives the per-block loop's codes (mv:3406-3466, 4496-4508)."""
+    import numpy as np
+    from mvregfus_b200 import _host_workers as hw
+    from mvregfus_b200 import synthetic
+    shape = (96, 80, 120)
+    params = synthetic.view_params(shape, 4, seed=3, odd_extra_deg=7.0)
+    props = [{"size": np.array(shape), "spacing": np.ones(3), "origin": np.zeros(3)} for _ in range(4)]
+    sp_origin, size, qspacing = np.array([-20.0, -10.0, -30.0]), 16, np.array([2.0, 2.0, 2.0])
+    locs = list(np.ndindex(5, 4, 6))
+    loop = hw.block_codes_chunk((locs, sp_origin, size, qspacing, props, params))
+    origins = sp_origin + np.array(locs, dtype=np.int64) * size * qspacing
+    fast = hw.block_codes_all(props, params, origins, np.array([size] * 3).astype(np.int64), qspacing, 2)
+    assert np.array_equal(loop, fast)
+    assert set(np.unique(fast)) == {0, 1, 2}

@@ -69,12 +69,22 @@ def config2(dev, rank, world, views=None, params=None, props=None):
         M, off = mv.index_space_affine(params[v], props[v]["spacing"], props[v]["origin"], sp["spacing"], sp["origin"])
         tv.append(fusion.affine_resample(views[v], M, off, (512, 1024, 1024), rule="scipy"))
     torch.cuda.synchronize()
+    if rank == 0:   # rank 0 fits the coarse grid for everybody: it may use all host cores (worker processes started up front)
+        from mvregfus_b200 import _hostpool
+        os.environ["MVF_HOST_WORKERS"] = str(max(0, min(16, len(os.sched_getaffinity(0)) - 2)))
+        if _hostpool.workers() >= 2:
+            _hostpool._start(_hostpool.workers())
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     ws, b, size = dct.quality_grid(tv, params, props, sp)      # every rank computes the (tiny) grid: no exchange
     torch.cuda.synchronize()
     t_q = time.perf_counter() - t0
     t0 = time.perf_counter()
-    coarse = dct.coarse_weights(ws, sp, b, size)
+    box = [dct.coarse_weights(ws, sp, b, size) if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)   # a (V, 8, 16, 16) float64 grid + two 3-vectors
+    coarse = box[0]
     t_c = time.perf_counter() - t0
     del tv
     vs = fusion.build_viewset(views, props, params, sp, weights="dct", coarse=coarse)
