@@ -58,12 +58,14 @@ struct AxArgs {
   WTab* wtab;
 };
 
-enum { AW_ZERO = 0, AW_ONE = 1, AW_Z = 2, AW_Y = 3, AW_X = 4, AW_3D = 5 };
+// weight class of a view on a tile: which fused axes leave the all-ones plateau of the blending field there
+enum { AW_ZERO = 0, AW_ONE = 1, AW_Z = 2, AW_Y = 3, AW_X = 4, AW_3D = 5, AW_ZT = 6 /* z and one of y / x */, AW_YX = 7 };
 
 struct AxTile {
   int b0[3];   // view index of brick element (0,0,0); b0[a] belongs to view axis vax[a]
   int skip;    // the tile sees no voxel of the view (or its weight is 0 everywhere): nothing to gather
   int wcls;    // AW_*
+  int wactive; // bit a set: fused axis a leaves the plateau somewhere in the tile
   int corr;    // element offset of brick element (0,0,0) in the absolute offsets of the tables
   int regular; // the z walk never jumps over a plane inside this tile
   int unit;    // ... and moves on by exactly one plane at every step
@@ -212,7 +214,10 @@ __device__ __forceinline__ void ax_make_tile(const AxArgs& X, int v, const int l
     }
   }
   t.corr = corr;
-  t.wcls = zero ? AW_ZERO : (active == 0 ? AW_ONE : (active == 1 ? AW_Z : (active == 2 ? AW_Y : (active == 4 ? AW_X : AW_3D))));
+  // bit 0 = z, 1 = y, 2 = x active
+  t.wcls = zero ? AW_ZERO : (active == 0 ? AW_ONE : (active == 1 ? AW_Z : (active == 2 ? AW_Y : (active == 4 ? AW_X :
+           (active == 6 ? AW_YX : (active == 7 ? AW_3D : AW_ZT))))));
+  t.wactive = active;
   t.skip = skip || zero;
 }
 
@@ -296,7 +301,18 @@ __device__ __forceinline__ void ax_walk_window(const GTab* __restrict__ gz_tab, 
 }
 
 // ---- weighting and accumulation of one view's values -----------------------------------------------------------
-enum { WC_NORMALISED = 0, WC_THREAD = 1, WC_ZTABLE = 2, WC_FIELD = 3 };
+// Two active axes: the third profile is 1 on the whole tile, min(f_a, f_b, 1) = min(f_a, f_b), and the lerp along the
+// plateau axis is a lerp of equal values (exact) - same bits as ax_weight_3d at a third of the instructions.
+// `eo` = entry of the outer (slower) axis, `ei` = entry of the inner one, in z, y, x nesting order.
+__device__ __forceinline__ float ax_weight_2d(const WTab& eo, const WTab& ei) {
+  const float v00 = fminf(eo.v0, ei.v0), v01 = fminf(eo.v0, ei.v1), v10 = fminf(eo.v1, ei.v0), v11 = fminf(eo.v1, ei.v1);
+  const float i0 = fmaf(v01 - v00, ei.t, v00);
+  const float i1 = fmaf(v11 - v10, ei.t, v10);
+  const float w = fmaf(i1 - i0, eo.t, i0);
+  return (eo.t >= 0.f && ei.t >= 0.f) ? w : 0.f;
+}
+
+enum { WC_NORMALISED = 0, WC_THREAD = 1, WC_ZTABLE = 2, WC_FIELD = 3, WC_ZT = 4 };
 
 // WC selects where the blending weight comes from (one uniform branch per view instead of one per voxel).
 template <typename T, int WC, bool WANT_F32>
@@ -309,6 +325,7 @@ __device__ __forceinline__ void ax_accumulate(const float (&val)[AZ], const WTab
     if (WC == WC_NORMALISED) wn = wconst;
     else if (WC == WC_THREAD) wn = div_by(wconst, S[k], rS[k]);
     else if (WC == WC_ZTABLE) wn = div_by(wz_tab[k].w1, S[k], rS[k]);
+    else if (WC == WC_ZT) wn = div_by(ax_weight_2d(wz_tab[k], ey), S[k], rS[k]);   // `ey` = the active one of the thread's two entries
     else wn = div_by(ax_weight_3d(wz_tab[k], ey, ex), S[k], rS[k]);
     float vv = val[k];
     if (sizeof(T) == 2) vv = u16_to_float(round_half_up_u16(vv));
@@ -418,8 +435,13 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
         const WTab ey = wt[v][AZ + ty], ex = wt[v][AZ + AY + tx];
 #pragma unroll
         for (int k = 0; k < AZ; ++k) S[k] += ax_weight_3d(wt[v][k], ey, ex);
+      } else if (cls == AW_ZT) {
+        const WTab et = (tv[v].wactive & 2) ? wt[v][AZ + ty] : wt[v][AZ + AY + tx];
+#pragma unroll
+        for (int k = 0; k < AZ; ++k) S[k] += ax_weight_2d(wt[v][k], et);
       } else {
-        const float w = cls == AW_ONE ? 1.f : (cls == AW_Y ? wt[v][AZ + ty].w1 : wt[v][AZ + AY + tx].w1);
+        const float w = cls == AW_ONE ? 1.f : (cls == AW_Y ? wt[v][AZ + ty].w1 : (cls == AW_X ? wt[v][AZ + AY + tx].w1
+                                                 : ax_weight_2d(wt[v][AZ + ty], wt[v][AZ + AY + tx])));
 #pragma unroll
         for (int k = 0; k < AZ; ++k) S[k] += w;
       }
@@ -451,7 +473,8 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
     const bool regular = tv[v].regular != 0;
     const int dsz = av.dsz;
     const WTab ey = wt[v][AZ + ty], ex = wt[v][AZ + AY + tx];
-    const float wthread = cls == AW_Y ? ey.w1 : (cls == AW_X ? ex.w1 : 1.f);
+    const float wthread = cls == AW_Y ? ey.w1 : (cls == AW_X ? ex.w1 : (cls == AW_YX ? ax_weight_2d(ey, ex) : 1.f));
+    const WTab et = (tv[v].wactive & 2) ? ey : ex;   // AW_ZT: the thread's entry along the active one of y / x
     auto plane = [&](int off) {
       const float a = tap<T>(p00, off), bb = tap<T>(p01, off), c = tap<T>(p10, off), d = tap<T>(p11, off);
       const float r0 = fmaf(tX, bb, oX * a), r1 = fmaf(tX, d, oX * c);
@@ -472,6 +495,7 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
     if (uniform) ax_accumulate<T, WC_NORMALISED, WANT_F32>(val, wt[v], wn_uniform, ey, ex, S, rS, acc, accf);
     else if (cls == AW_Z) ax_accumulate<T, WC_ZTABLE, WANT_F32>(val, wt[v], 0.f, ey, ex, S, rS, acc, accf);
     else if (cls == AW_3D) ax_accumulate<T, WC_FIELD, WANT_F32>(val, wt[v], 0.f, ey, ex, S, rS, acc, accf);
+    else if (cls == AW_ZT) ax_accumulate<T, WC_ZT, WANT_F32>(val, wt[v], 0.f, et, ex, S, rS, acc, accf);
     else ax_accumulate<T, WC_THREAD, WANT_F32>(val, wt[v], wthread, ey, ex, S, rS, acc, accf);
     // The buffer goes back to the TMA once every warp has left it; only the issuing thread waits for that, the other
     // warps move on to the next view (whose brick sits in the other buffer) without a CTA-wide barrier.
@@ -607,6 +631,15 @@ static int try_fuse_axis(int nviews, const mvf_view* hv, const KArgs& A, cudaStr
   const size_t smem = 2 * (size_t)X.brick_stride + 128;
   // per-axis tables: stream-ordered scratch, filled by one small kernel in front of the fused kernel
   const size_t nent = (size_t)nviews * ((size_t)A.dims[0] + A.dims[1] + A.dims[2]);
+  static thread_local int pool_ready_dev = -1;   // keep the stream-ordered pool's memory across synchronisations
+  int cur_dev = 0;
+  MVF_CUDA(cudaGetDevice(&cur_dev));
+  if (pool_ready_dev != cur_dev) {
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, cur_dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pool_ready_dev = cur_dev;
+  }
   void* scratch = nullptr;
   MVF_CUDA(cudaMallocAsync(&scratch, nent * (sizeof(GTab) + sizeof(WTab)), st));
   X.gtab = reinterpret_cast<GTab*>(scratch);
