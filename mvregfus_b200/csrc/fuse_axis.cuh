@@ -47,21 +47,10 @@ struct AxView {
   int xalign;    // elements per 16 bytes
   int dsz;       // signed stride of one step of the z walk: str[0] * sign(sc[0])
 };
-struct AxArgs {
-  AxView v[MVF_MAX_VIEWS];
-  void* out;
-  float* outf;
-  int dims[3], org[3];
-  int nviews;
-  int brick_stride;   // bytes between the two brick buffers (multiple of 128)
-  GTab* gtab;         // per-axis tables of the box, view-major then z | y | x (ax_tables_kernel)
-  WTab* wtab;
-};
-
 // weight class of a view on a tile: which fused axes leave the all-ones plateau of the blending field there
 enum { AW_ZERO = 0, AW_ONE = 1, AW_Z = 2, AW_Y = 3, AW_X = 4, AW_3D = 5, AW_ZT = 6 /* z and one of y / x */, AW_YX = 7 };
 
-struct AxTile {
+struct __align__(16) AxTile {
   int b0[3];   // view index of brick element (0,0,0); b0[a] belongs to view axis vax[a]
   int skip;    // the tile sees no voxel of the view (or its weight is 0 everywhere): nothing to gather
   int wcls;    // AW_*
@@ -69,7 +58,22 @@ struct AxTile {
   int corr;    // element offset of brick element (0,0,0) in the absolute offsets of the tables
   int regular; // the z walk never jumps over a plane inside this tile
   int unit;    // ... and moves on by exactly one plane at every step
+  int pad[3];
 };
+static_assert(sizeof(AxTile) == 48, "tile records move as three 16-byte vectors");
+
+struct AxArgs {
+  AxView v[MVF_MAX_VIEWS];
+  void* out;
+  float* outf;
+  int dims[3], org[3];
+  int nviews;
+  int brick_stride;   // bytes between the two brick buffers (multiple of 128)
+  AxTile* tiles;      // per (tile, view) geometry and weight class (ax_tiles_kernel), tile-major
+  GTab* gtab;         // per-axis tables of the box, view-major then z | y | x (ax_tables_kernel)
+  WTab* wtab;
+};
+
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX) ---------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -107,9 +111,8 @@ __device__ __forceinline__ float div_by(float w, float s, float rs) {
   return fmaf(fmaf(-q, s, w), rs, q);
 }
 
-__device__ __forceinline__ bool ax_tile_origin(const int dims[3], int& z0, int& y0, int& x0) {
+__device__ __forceinline__ bool ax_tile_origin(const int dims[3], unsigned b, int& z0, int& y0, int& x0) {
   const unsigned snx = (dims[2] + AX * AST - 1) / (AX * AST), sny = (dims[1] + AY * AST - 1) / (AY * AST);
-  const unsigned b = blockIdx.x;
   const unsigned inner = b & (AST * AST * AST - 1), sup = b / (AST * AST * AST);
   const unsigned sx = sup % snx, sy = (sup / snx) % sny, sz = sup / (snx * sny);
   x0 = (int)((sx * AST + (inner & 3)) * AX);
@@ -221,6 +224,30 @@ __device__ __forceinline__ void ax_make_tile(const AxArgs& X, int v, const int l
   t.skip = skip || zero;
 }
 
+// One thread per (tile, view): everything a tile needs to know about a view before it can request its brick, so that
+// the fused kernel's first action per view is one 48-byte load instead of table look-ups and integer logic.
+__global__ void __launch_bounds__(128) ax_tiles_kernel(const __grid_constant__ AxArgs X, unsigned ntiles) {
+  const unsigned e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= ntiles * (unsigned)X.nviews) return;
+  const unsigned tile = e / X.nviews;
+  const int v = (int)(e - tile * X.nviews);
+  int z0, y0, x0;
+  AxTile t;
+  if (!ax_tile_origin(X.dims, tile, z0, y0, x0)) return;
+  const int loc0[3] = {z0, y0, x0};
+  ax_make_tile(X, v, loc0, t);
+  const int ntot = X.dims[0] + X.dims[1] + X.dims[2];
+  bool regular = true, unit = true;   // z walk of this view inside the tile (step k = 1 .. AZ-1)
+  for (int k = 1; k < AZ; ++k) {
+    const int code = z0 + k < X.dims[0] ? (X.gtab[(size_t)v * ntot + z0 + k].mode & 3) : 0;
+    regular = regular && code != 3;
+    unit = unit && code == 1;
+  }
+  t.regular = regular; t.unit = unit;
+  t.pad[0] = t.pad[1] = t.pad[2] = 0;
+  X.tiles[e] = t;
+}
+
 // ITK-linear sample of min(f_z, f_y, f_x) from the three per-axis entries (lerp x, then y, then z)
 __device__ __forceinline__ float ax_weight_3d(const WTab& ez, const WTab& ey, const WTab& ex) {
   const float m00 = fminf(ez.v0, ey.v0), m01 = fminf(ez.v0, ey.v1), m10 = fminf(ez.v1, ey.v0), m11 = fminf(ez.v1, ey.v1);
@@ -242,13 +269,16 @@ __device__ __forceinline__ float ax_weight_3d(const WTab& ez, const WTab& ey, co
 // (trailing, leading) is carried along.  REGULAR walks (never more than one plane per step) are straight-line code: the
 // new plane is always loaded and the pair moves by predicated selects, so the loads of step k+1 overlap the arithmetic
 // of step k.
-template <bool REGULAR, typename Plane>
+template <bool REGULAR, bool UNIT, typename Plane>
 __device__ __forceinline__ void ax_walk_planes(const GTab* __restrict__ gz_tab, Plane plane, int dsz, float (&val)[AZ]) {
   float Pl = 0.f, Pd = plane(gz_tab[0].off - dsz);   // trailing plane of the first step
 #pragma unroll
   for (int k = 0; k < AZ; ++k) {
     const GTab gz = gz_tab[k];   // uniform over the CTA: one broadcast LDS.128
-    if (REGULAR) {
+    if (UNIT) {            // every step moves on by exactly one plane: no selects
+      Pl = Pd;
+      Pd = plane(gz.off);
+    } else if (REGULAR) {
       const float np = plane(gz.off);
       const bool adv = gz.mode != 0;
       Pl = adv ? Pd : Pl;
@@ -350,7 +380,7 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
   __shared__ int live[MVF_MAX_VIEWS], nlive_s, nweight_s, uniform_s;
 
   int z0, y0, x0;
-  if (!ax_tile_origin(X.dims, z0, y0, x0)) return;
+  if (!ax_tile_origin(X.dims, blockIdx.x, z0, y0, x0)) return;
   const int tid = threadIdx.x;
   // TMA destinations must be 128-byte aligned whatever the static shared memory adds up to
   unsigned char* const bricks = ax_smem + ((128u - (smem_u32(ax_smem) & 127u)) & 127u);
@@ -369,17 +399,15 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
   const int loc0[3] = {z0, y0, x0};
   if (tid >= ANT - 32) {
     const int lane = tid - (ANT - 32);
-    if (lane < X.nviews) ax_make_tile(X, lane, loc0, tv[lane]);
-    {  // does the z walk of a view jump over a plane inside this tile?  (lane k looks at step k)
-      const int ntot = X.dims[0] + X.dims[1] + X.dims[2];
-      const int li = z0 + lane;
-      for (int v = 0; v < X.nviews; ++v) {
-        int code = 1;   // lanes that are not a step of this tile vote "moved by one"
-        if (lane > 0 && lane < AZ) code = li < X.dims[0] ? (X.gtab[(size_t)v * ntot + li].mode & 3) : 0;
-        const unsigned jumps = __ballot_sync(0xffffffffu, code == 3), ones = __ballot_sync(0xffffffffu, code == 1);
-        if (lane == 0) { tv[v].regular = jumps == 0u; tv[v].unit = ones == 0xffffffffu; }
-      }
+    if (lane == 0) {   // independent of the records: overlaps their load
+      mbar_init(&mbar[0], 1);
+      mbar_init(&mbar[1], 1);
+      mbar_init(&mfree[0], ANT / 32);
+      mbar_init(&mfree[1], ANT / 32);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (lane < X.nviews) tv[lane] = X.tiles[(size_t)blockIdx.x * X.nviews + lane];
     __syncwarp();
     if (lane == 0) {
       int n = 0, nw = 0, uni = 1;
@@ -389,12 +417,6 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
         if (tv[v].wcls > AW_ONE) uni = 0;
       }
       nlive_s = n; nweight_s = nw; uniform_s = uni;
-      mbar_init(&mbar[0], 1);
-      mbar_init(&mbar[1], 1);
-      mbar_init(&mfree[0], ANT / 32);
-      mbar_init(&mfree[1], ANT / 32);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       for (int b = 0; b < 2 && b < n; ++b) issue(live[b], b);
     }
   } else {
@@ -487,10 +509,12 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
                   *q10 = reinterpret_cast<const float*>(p10), *q11 = reinterpret_cast<const float*>(p11);
       if (dsz > 0) ax_walk_window<true>(gt[v], q00, q01, q10, q11, tX, oX, tY, oY, val);
       else ax_walk_window<false>(gt[v], q00, q01, q10, q11, tX, oX, tY, oY, val);
+    } else if (tv[v].unit) {
+      ax_walk_planes<true, true>(gt[v], plane, dsz, val);
     } else if (regular) {
-      ax_walk_planes<true>(gt[v], plane, dsz, val);
+      ax_walk_planes<true, false>(gt[v], plane, dsz, val);
     } else {
-      ax_walk_planes<false>(gt[v], plane, dsz, val);
+      ax_walk_planes<false, false>(gt[v], plane, dsz, val);
     }
     if (uniform) ax_accumulate<T, WC_NORMALISED, WANT_F32>(val, wt[v], wn_uniform, ey, ex, S, rS, acc, accf);
     else if (cls == AW_Z) ax_accumulate<T, WC_ZTABLE, WANT_F32>(val, wt[v], 0.f, ey, ex, S, rS, acc, accf);
@@ -641,11 +665,14 @@ static int try_fuse_axis(int nviews, const mvf_view* hv, const KArgs& A, cudaStr
     pool_ready_dev = cur_dev;
   }
   void* scratch = nullptr;
-  MVF_CUDA(cudaMallocAsync(&scratch, nent * (sizeof(GTab) + sizeof(WTab)), st));
+  const unsigned ntiles = ax_tile_grid(A.dims).x;
+  MVF_CUDA(cudaMallocAsync(&scratch, nent * (sizeof(GTab) + sizeof(WTab)) + (size_t)ntiles * nviews * sizeof(AxTile), st));
   X.gtab = reinterpret_cast<GTab*>(scratch);
   X.wtab = reinterpret_cast<WTab*>(X.gtab + nent);
+  X.tiles = reinterpret_cast<AxTile*>(X.wtab + nent);
   ax_tables_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, st>>>(X);
-  mvf::launch_counter()++;
+  ax_tiles_kernel<<<(ntiles * nviews + 127) / 128, 128, 0, st>>>(X, ntiles);
+  mvf::launch_counter() += 2;
   auto launch = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
