@@ -35,6 +35,11 @@ template <int CW> __device__ __forceinline__ void vec_store(float* p, const floa
   if constexpr (CW == 4) *reinterpret_cast<V*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   else *reinterpret_cast<V*>(p) = make_float2(v[0], v[1]);
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -217,8 +222,11 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
   const bool have_w = wts != nullptr;
 #pragma unroll
   for (int i = 0; i < CW; ++i) eW[i] = 1.f;
-  auto load_operands = [&](int z) {
-    const size_t o = (size_t)z * plane + i0;
+  // Plane offsets are running 64-bit sums (one add per step) or one 32 x 32 -> 64 bit multiply of a plane index, never a
+  // 64 x 64 bit product: address arithmetic was a quarter of this kernel's instructions.
+  const unsigned plane32 = (unsigned)plane;
+  auto in_plane = [&](int zm) { return A.in + ((size_t)((unsigned long long)(unsigned)zm * plane32) + i0); };
+  auto load_operands = [&](size_t o) {
     if (have_w) vec_load<CW>(wts + o, eW);
     if (MODE == RL_RATIO) {
       if (A.view_u16) {
@@ -238,14 +246,14 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
       if (A.last) vec_load<CW>(est + o, eI);
     }
   };
-  vec_load<CW>(A.in + (size_t)__ldg(zmap + zo0 - R) * plane + i0, pn);
-  if (MODE != RL_PLAIN && R == 0) load_operands(zo0);
-  for (int t = zo0 - R; t < zo1 + R; ++t) {
+  vec_load<CW>(in_plane(__ldg(zmap + zo0 - R)), pn);
+  if (MODE != RL_PLAIN && R == 0) load_operands((size_t)zo0 * plane + i0);
+  size_t o = (size_t)((long long)(zo0 - 2 * R) * (long long)plane) + i0;   // offset of output plane z = t - R (meaningful once z >= zo0)
+  for (int t = zo0 - R; t < zo1 + R; ++t, o += plane) {
     const int z = t - R;
     const bool emit = z >= zo0;
-    const size_t o = (size_t)z * plane + i0;
     if (RLS_AHEAD > 0 && t + RLS_AHEAD < zo1 + R) {
-      prefetch_l2(A.in + (size_t)__ldg(zmap + t + RLS_AHEAD) * plane + i0);
+      prefetch_l2(in_plane(__ldg(zmap + t + RLS_AHEAD)));
       if (MODE != RL_PLAIN && z + RLS_AHEAD >= zo0) {   // epilogue operands of the plane completed RLS_AHEAD steps from now
         const size_t oa = o + (size_t)RLS_AHEAD * plane;
         if (have_w) prefetch_l2(wts + oa);
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
     }
 #pragma unroll
     for (int i = 0; i < CW; ++i) p[i] = pn[i];
-    if (t + 1 < zo1 + R) vec_load<CW>(A.in + (size_t)__ldg(zmap + t + 1) * plane + i0, pn);
+    if (t + 1 < zo1 + R) vec_load<CW>(in_plane(__ldg(zmap + t + 1)), pn);
     float e[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
         if (MODE == RL_PLAIN) {
           r[i] = blur;
         } else if (MODE == RL_RATIO) {
-          const float ratio = __fdividef(eI[i], blur + 1e-6f);
+          const float ratio = eI[i] * rcp_approx(blur + 1e-6f);   // divisor >= 1e-6: no denormal / huge-divisor guards needed
           r[i] = eW[i] > 1e-5f ? ratio : 0.f;
         } else {
           const float ow = blur * eW[i];
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(RLS_NT, MVF_RLS_MINB) rl_z_kernel(const __grid
       if (active) vec_store<CW>((MODE == RL_CORRECT && A.last) ? est + o : outp + o, r);
     }
     // operands of the plane the next step completes
-    if (MODE != RL_PLAIN && z + 1 >= zo0 && z + 1 < zo1) load_operands(z + 1);
+    if (MODE != RL_PLAIN && z + 1 >= zo0 && z + 1 < zo1) load_operands(o + plane);
   }
   if (MODE == RL_CORRECT && A.last && A.sum) {
 #pragma unroll
