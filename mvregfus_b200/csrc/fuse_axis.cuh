@@ -105,6 +105,14 @@ template <typename T> __device__ __forceinline__ float tap(const T* p, int off);
 template <> __device__ __forceinline__ float tap<float>(const float* p, int off) { return p[off]; }
 template <> __device__ __forceinline__ float tap<uint16_t>(const uint16_t* p, int off) { return u16_to_float(p[off]); }
 
+// 1 / s to within an ulp for s in [~1e-3, 8] (sums of blending weights): hardware approximation + one Newton step,
+// without the special-case path of the IEEE reciprocal
+__device__ __forceinline__ float rcp_newton(float s) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s));
+  return fmaf(y, fmaf(-s, y, 1.f), y);
+}
+
 // RN(w / s) from rs = RN(1 / s): one product, one exact residual, one correction (Markstein)
 __device__ __forceinline__ float div_by(float w, float s, float rs) {
   const float q = w * rs;
@@ -471,7 +479,7 @@ fuse_axis_kernel(const __grid_constant__ TmaMaps TM, const __grid_constant__ AxA
 #pragma unroll
     for (int k = 0; k < AZ; ++k) {
       S[k] = S[k] == 0.f ? 1.f : S[k];
-      rS[k] = __frcp_rn(S[k]);
+      rS[k] = rcp_newton(S[k]);
     }
   }
 

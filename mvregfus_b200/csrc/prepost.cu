@@ -254,7 +254,7 @@ extern "C" int mvf_bin_shrink(const void* in, int dtype, const int32_t in_dims[3
   const int grid = stream_grid((size_t)o[0] * o[1] * o[2]);
   cudaStream_t st = as_stream(stream);
   const bool al = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
-  if (dtype == MVF_U16 && factors[2] == 2 && in_dims[2] % 16 == 0 && al && factors[0] * factors[1] <= 16384)
+  if (dtype == MVF_U16 && factors[2] == 2 && in_dims[2] % 16 == 0 && al && factors[0] * factors[1] <= 4096)   // div_small is exact below 2^31: 2 * 65535 * 2 * fz * fy must stay there
     bin_shrink_x2_u16_kernel<<<stream_grid((size_t)o[0] * o[1] * (o[2] / 4)), 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, in_dims[1], in_dims[2], o[0], o[1], o[2], factors[0], factors[1]);
   else if (dtype == MVF_U16)
     bin_shrink_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)in, (uint16_t*)out, in_dims[1], in_dims[2], o[0], o[1], o[2], factors[0], factors[1], factors[2]);

@@ -178,6 +178,10 @@ extern "C" int mvf_rl_fft_padded_dims(const int32_t dims[3], const int32_t ksize
 extern "C" int mvf_rl_fft_plan_create(const int32_t dims[3], const int32_t ksize[3], void* workspace_or_null,
                                       size_t* workspace_bytes, void** plan_out) {
   MVF_CHECK_ARG(dims && ksize && plan_out && workspace_bytes, "NULL argument");
+  // the closed-form y/x index map (wrap into the far reflected tail) needs n >= K + 3; z goes through the caller's plane map
+  for (int d = 1; d < 3; ++d)
+    if (dims[d] < ksize[d] + 3)
+      return fail(MVF_ERR_UNSUPPORTED, "%s%s", "rl: volume extent smaller than PSF size + 3 (the reference's reflect padding needs it)");
   FftPlan* p = new FftPlan();
   for (int d = 0; d < 3; ++d) {
     p->n[d] = dims[d];

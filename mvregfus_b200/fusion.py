@@ -214,6 +214,11 @@ def build_viewset(tensors, orig_stack_propertiess, params, stack_properties, wei
             vs.keep.append(g)
             s.cgrid = g.data_ptr()
             s.cdims = _cabi.i32x3(g.shape)
+            if np.any(out_sp / np.asarray(c_sp, dtype=np.float64) > 0.25 + 1e-12):
+                # the kernels cache 4 coarse planes per 8-voxel column: DCT blocks of fewer than 4 fused voxels
+                # (size * bin < 4, only for spacings beyond ~25 um) are not supported
+                raise ValueError("DCT weight grid too fine for the fused kernels: block edge %s fused voxels (< 4)"
+                                 % (np.asarray(c_sp, dtype=np.float64) / out_sp,))
             s.cscale = _cabi.f64(out_sp / np.asarray(c_sp, dtype=np.float64), 3)
             s.coffset = _cabi.f64((out_or - np.asarray(c_or, dtype=np.float64)) / np.asarray(c_sp, dtype=np.float64), 3)
             s.weight_mode = _cabi.MVF_W_BLEND_DCT

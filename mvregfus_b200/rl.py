@@ -29,12 +29,24 @@ def factor_psf(psf, tol=2e-6):
     return (kz / total).astype(np.float32), (ky / total).astype(np.float32), kx.astype(np.float32)
 
 
+def too_long_for_kernels(psf):
+    """PSFs longer than MVF_RL_KMAX taps per axis (sz / spacing large) only fit the cuFFT convolution."""
+    return int(max(np.asarray(psf).shape)) > _cabi.MVF_RL_KMAX
+
+
+def fft_only_psf_struct(psf):
+    """PSF struct of a view that always goes through cuFFT: only the sizes are used (index map of the z halo)."""
+    s = _cabi.MvfRlPsf()
+    s.ksize = _cabi.i32x3(np.asarray(psf).shape)
+    return s
+
+
 def make_dense_psf_struct(psf, device):
     """Non-separable PSF: centred, zero padded to Kp^3 and uploaded; returns (struct, tensor to keep alive)."""
     psf = np.asarray(psf, dtype=np.float32)
     kp = _cabi.load().mvf_rl_padded_size(int(max(psf.shape)))
     if kp < 0 or any(k % 2 == 0 for k in psf.shape):
-        raise ValueError("PSF sizes must be odd and <= %d" % _cabi.MVF_RL_KMAX)
+        raise ValueError("PSF sizes must be odd and <= %d for the direct kernel" % _cabi.MVF_RL_KMAX)
     full = np.zeros((kp, kp, kp), dtype=np.float32)
     o = [(kp - k) // 2 for k in psf.shape]
     full[o[0]:o[0] + psf.shape[0], o[1]:o[1] + psf.shape[1], o[2]:o[2] + psf.shape[2]] = psf
@@ -172,12 +184,23 @@ class RLPlan:
         self.radii, self.spectra, self.fft = [], [], None
         self.dense_mode = os.environ.get("MVF_RL_DENSE", "fft")  # 'fft' (cuFFT) or 'direct' (O(K^3) kernel)
         for p in psfs:
-            f = factor_psf(p)
+            if any(n < k + 3 for n, k in zip(self.dims, np.asarray(p).shape)):
+                raise ValueError("volume extents %s are smaller than PSF size + 3 (%s): the reference's reflect padding "
+                                 "needs that much" % (self.dims, np.asarray(p).shape))
+            f = None if too_long_for_kernels(p) else factor_psf(p)
             self.separable.append(f is not None)
             spec = None
             if f is not None:  # outer-product PSF (axis-aligned view): fused separable kernel
                 self.psf_structs.append(make_psf_struct(f))
                 ksz, rp = len(f[0]), padded_radius(f)
+            elif too_long_for_kernels(p) and self.dense_mode == "fft":   # more taps than the convolution kernels hold
+                if any(k % 2 == 0 for k in np.asarray(p).shape):
+                    raise ValueError("PSF sizes must be odd")
+                self.psf_structs.append(fft_only_psf_struct(p))
+                ksz, rp = int(np.asarray(p).shape[0]), (int(np.asarray(p).shape[0]) - 1) // 2
+                if self.fft is None:
+                    self.fft = FftBlur(self.dims, np.asarray(p).shape, dev)
+                spec = self.fft.spectrum(np.asarray(p))
             else:              # oblique view: dense PSF -> cuFFT convolution (or the direct kernel on request)
                 st, keep = make_dense_psf_struct(p, dev)
                 self.psf_structs.append(st)
@@ -351,11 +374,17 @@ class SlabRLPlan:
         dense_mode = os.environ.get("MVF_RL_DENSE", "fft")
         rp = None
         for p in psfs:
-            f = factor_psf(p)
+            f = None if too_long_for_kernels(p) else factor_psf(p)
             spec = None
             if f is not None:
                 self.psf_structs.append(make_psf_struct(f))
                 r = padded_radius(f)
+            elif too_long_for_kernels(p) and dense_mode == "fft":
+                self.psf_structs.append(fft_only_psf_struct(p))
+                r = (int(np.asarray(p).shape[0]) - 1) // 2
+                if self.fft is None:
+                    self.fft = FftBlur((nzl, ny, nx), np.asarray(p).shape, dev)
+                spec = self.fft.spectrum(np.asarray(p))
             else:
                 st, keep = make_dense_psf_struct(p, dev)
                 self.psf_structs.append(st)

@@ -238,3 +238,24 @@ def test_rl_block_sum_and_convergence_break(cuda):
     assert plan2.iterations_run == n_ref
     err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
     assert float(err.max()) <= 1e-3, float(err.max())
+
+
+def test_rl_psf_longer_than_kernel_limit_uses_fft(cuda):
+    """get_psf yields ~3 * sz / spacing taps: at fine spacings that exceeds the 43 taps the convolution kernels hold.
+    Such PSFs (separable or not) run through the cuFFT convolution instead of raising, like the reference (mv:5647-5673)."""
+    from mvregfus_b200 import fusion, rl
+    rng = np.random.default_rng(4)
+    shape = (112, 56, 64)   # every extent >= taps + 3, as the reference's padding needs
+    tv = [(rng.random(shape) * 2000).astype(np.uint16) for _ in range(2)]
+    w = [np.full(shape, 0.5, dtype=np.float32) for _ in range(2)]
+    kz = np.exp(-0.5 * ((np.arange(45) - 22) / 7.0) ** 2)
+    kxy = np.exp(-0.5 * ((np.arange(45) - 22) / 1.5) ** 2)
+    psf = (kz[:, None, None] * kxy[None, :, None] * kxy[None, None, :])
+    psf = (psf / psf.sum()).astype(np.float32)
+    sp = {"size": np.array(shape), "spacing": np.ones(3), "origin": np.zeros(3)}
+    ref = O.fuse_LR_with_weights_np(tv, None, sp, num_iterations=3, weights=w, psfs=np.array([psf, psf]), return_float=True)
+    plan = rl.RLPlan([fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w], [psf, psf])
+    assert plan.fft is not None and not any(plan.streamed)
+    got = plan.run(num_iterations=3).cpu().numpy()
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+    assert float(err.max()) <= 1e-3, float(err.max())
