@@ -191,6 +191,23 @@ int mvf_rl_correct_z(const float* in, const int32_t* zmap, const int32_t dims[3]
                      const float* weights, float* corr, int first, int last, float* est, int64_t est_offset,
                      double* sum_out, void* stream);
 
+/* Second blur with its z pass first (the passes of a separable blur commute), so that the ratio volume never reaches
+ * HBM: mvf_rl_zz turns T1 = mvf_rl_xy(estimate) into T2 = blur_z(I / (max(blur_z(T1), 0) + 1e-6)) with two shift
+ * registers per column; mvf_rl_xy_correct runs the x/y passes on T2 and applies max(., 0) and the correction epilogue
+ * of mvf_rl_correct to every finished row (mv:5686-5723).
+ * The two plane maps are HOST arrays: they are piecewise affine and travel in the kernel parameters as (at most 8) runs
+ * of constant step (MVF_ERR_UNSUPPORTED beyond that):
+ *   zmap1 (host, dims[0] + 4*Rp): extended position s in [-2Rp, dims[0] + 2Rp) -> plane of t1;
+ *   rmap  (host, dims[0] + 2*Rp): extended position t in [-Rp, dims[0] + Rp) -> plane of `view` (>= 0), or -1 - k:
+ *   the ratio at t is plane k of `side` (positions outside the volume repeat ratios of planes near the top - reflect
+ *   above, wrap below - which the caller computes first with mvf_rl_ratio_z on those planes).  `view` must already be
+ *   zero wherever the weight is <= 1e-5 (the mask of mv:5695-5699). */
+int mvf_rl_zz(const float* t1, const int32_t* host_zmap1, const int32_t* host_rmap, const int32_t dims[3], const mvf_rl_psf* psf,
+              const void* view, int dtype, const float* side, float* t2_out, void* stream);
+int mvf_rl_xy_correct(const float* t2, int32_t nplanes, const int32_t dims[3], const mvf_rl_psf* psf,
+                      const float* weights, float* corr, int first, int last, float* est, int64_t est_offset,
+                      double* sum_out, void* stream);
+
 /* ---- RL, general PSFs: cuFFT circular convolution with the reference's padding (mv:5647-5673) ------------
  * For PSFs that are not outer products (oblique views).  The padded extents are the next 2^a3^b5^c7^d >=
  * n + K - 1 per axis (the reference uses n + K + 1; the extra entries only hold zeros, the reflected tail and

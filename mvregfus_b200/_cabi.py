@@ -25,6 +25,7 @@ EXPORTS = (
     "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
     "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur",
     "mvf_rl_stream_supported", "mvf_rl_xy", "mvf_rl_blur_z", "mvf_rl_ratio_z", "mvf_rl_correct_z",
+    "mvf_rl_zz", "mvf_rl_xy_correct",
     "mvf_subsample", "mvf_range_u16", "mvf_hist_u16", "mvf_background_u16", "mvf_bin_shrink",
 )
 MVF_RL_KMAX = 43
@@ -93,6 +94,9 @@ def _declare(lib):
     lib.mvf_rl_blur_z.argtypes = lib.mvf_rl_blur.argtypes
     lib.mvf_rl_ratio_z.argtypes = lib.mvf_rl_ratio.argtypes
     lib.mvf_rl_correct_z.argtypes = lib.mvf_rl_correct.argtypes
+    lib.mvf_rl_zz.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32p, psfp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_xy_correct.argtypes = [C.c_void_p, C.c_int32, i32p, psfp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int64, C.c_void_p, C.c_void_p]
     lib.mvf_rl_fft_padded_dims.argtypes = [i32p, i32p, i32p]
     lib.mvf_rl_fft_plan_create.argtypes = [i32p, i32p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
     lib.mvf_rl_fft_plan_set_workspace.argtypes = [C.c_void_p, C.c_void_p]

@@ -413,15 +413,40 @@ static int launch_rl(int kp, const RLArgs& A, cudaStream_t st) {
 }
 
 // streaming two-kernel formulation (rl_stream.cuh): CW = 4 columns per thread up to 19 taps, 2 beyond
+template <int MODE>
 static int launch_rl_xy(int kp, const RLArgs& A, int nplanes, cudaStream_t st) {
   switch (kp) {
-    case 7: return launch_rl_xy_k<7, 4>(A, nplanes, st);
-    case 13: return launch_rl_xy_k<13, 4>(A, nplanes, st);
-    case 19: return launch_rl_xy_k<19, 4>(A, nplanes, st);
-    case 25: return launch_rl_xy_k<25, 2>(A, nplanes, st);
-    case 31: return launch_rl_xy_k<31, 2>(A, nplanes, st);
-    case 37: return launch_rl_xy_k<37, 2>(A, nplanes, st);
-    case 43: return launch_rl_xy_k<43, 2>(A, nplanes, st);
+    case 7: return launch_rl_xy_k<7, 4, MODE>(A, nplanes, st);
+    case 13: return launch_rl_xy_k<13, 4, MODE>(A, nplanes, st);
+    case 19: return launch_rl_xy_k<19, 4, MODE>(A, nplanes, st);
+    case 25: return launch_rl_xy_k<25, 2, MODE>(A, nplanes, st);
+    case 31: return launch_rl_xy_k<31, 2, MODE>(A, nplanes, st);
+    case 37: return launch_rl_xy_k<37, 2, MODE>(A, nplanes, st);
+    case 43: return launch_rl_xy_k<43, 2, MODE>(A, nplanes, st);
+    default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 43 taps");
+  }
+}
+
+// z pass + ratio + z pass (rl_zz_kernel): two shift registers per column.  Up to 19 taps: 4 columns per thread and one
+// 256-thread CTA per SM (MVF_RL_ZZ_CW=2: 2 columns, two CTAs); beyond: 2 columns per thread, one CTA per SM.
+static int zz_cw19() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVF_RL_ZZ_CW");
+    v = (e && atoi(e) == 2) ? 2 : 4;
+  }
+  return v;
+}
+static int launch_rl_zz(int kp, const RLZZArgs& A, cudaStream_t st) {
+  const bool wide = zz_cw19() == 4 && A.nx % 4 == 0;
+  switch (kp) {
+    case 7: return wide ? launch_rl_zz_k<7, 4, 2>(A, st) : launch_rl_zz_k<7, 2, 2>(A, st);
+    case 13: return wide ? launch_rl_zz_k<13, 4, 1>(A, st) : launch_rl_zz_k<13, 2, 2>(A, st);
+    case 19: return wide ? launch_rl_zz_k<19, 4, 1>(A, st) : launch_rl_zz_k<19, 2, 2>(A, st);
+    case 25: return launch_rl_zz_k<25, 2, 1>(A, st);
+    case 31: return launch_rl_zz_k<31, 2, 1>(A, st);
+    case 37: return launch_rl_zz_k<37, 2, 1>(A, st);
+    case 43: return launch_rl_zz_k<43, 2, 1>(A, st);
     default: return fail(MVF_ERR_UNSUPPORTED, "%s%s", "separable PSF longer than 43 taps");
   }
 }
@@ -447,7 +472,7 @@ static int fill_rl(RLArgs& A, const float* in, const int32_t* zmap, const int32_
   for (int d = 0; d < 3; ++d) {
     if (psf->ksize[d] < 1 || psf->ksize[d] > RL_KMAX || !(psf->ksize[d] & 1))
       return fail(MVF_ERR_INVALID, "%s%s", "rl: PSF sizes must be odd and <= 43");
-    if (dims[d] < psf->ksize[d] + 3)
+    if (d > 0 && dims[d] < psf->ksize[d] + 3)   // (z runs through the caller's plane map: slabs / plane ranges may be thinner)
       return fail(MVF_ERR_UNSUPPORTED, "%s%s", "rl: volume extent smaller than PSF size + 3 (the reference's reflect padding needs it)");
     kmax = psf->ksize[d] > kmax ? psf->ksize[d] : kmax;
   }
@@ -559,7 +584,7 @@ extern "C" int mvf_rl_xy(const float* in, int32_t nplanes, const int32_t dims[3]
   MVF_CHECK_ARG(!psf->dense, "the streaming kernels need a separable PSF");
   A.out = out;
   MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2), "rows must be 16-byte aligned (nx % 4 == 0; nx % 2 beyond 19 taps)");
-  return launch_rl_xy(kp, A, nplanes, as_stream(stream));
+  return launch_rl_xy<RL_PLAIN>(kp, A, nplanes, as_stream(stream));
 }
 
 extern "C" int mvf_rl_blur_z(const float* in, const int32_t* zmap, const int32_t dims[3], const mvf_rl_psf* psf,
@@ -602,4 +627,65 @@ extern "C" int mvf_rl_correct_z(const float* in, const int32_t* zmap, const int3
   MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2, weights, est ? est + est_offset : nullptr),
                 "buffers must be 16-byte aligned and nx a multiple of the vector width");
   return launch_rl_z<RL_CORRECT>(kp, A, as_stream(stream));
+}
+
+// ---- second blur with the z pass first: T1 -> (ratio) -> T2, then x/y passes + correction epilogue -----------------
+// runs of constant step of a host plane map (first position `first`): false if it needs more than ZZ_MAXSEG segments
+static bool compress_map(const int32_t* map, int n, int first, MapSeg* segs, int* nseg) {
+  int k = 0;
+  for (int i = 0; i < n;) {
+    if (k == ZZ_MAXSEG) return false;
+    int j = i + 1;
+    const int step = j < n ? map[j] - map[i] : 0;
+    while (j < n && map[j] - map[j - 1] == step) ++j;
+    segs[k].start = first + i; segs[k].base = map[i]; segs[k].step = step;
+    ++k;
+    i = j;
+  }
+  *nseg = k;
+  return true;
+}
+
+extern "C" int mvf_rl_zz(const float* t1, const int32_t* host_zmap1, const int32_t* host_rmap, const int32_t dims[3],
+                         const mvf_rl_psf* psf, const void* view, int dtype, const float* side, float* t2_out,
+                         void* stream) {
+  RLArgs B;
+  int kp;
+  const int32_t zm_dummy = 0;
+  int rc = fill_rl(B, t1, &zm_dummy, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(host_zmap1 && host_rmap && view && t2_out, "NULL argument");
+  MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
+  MVF_CHECK_ARG(!psf->dense, "the streaming kernels need a separable PSF");
+  B.out = t2_out;
+  const void* view_chk = dtype == MVF_U16 ? reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(view) * 2) : view;
+  MVF_CHECK_ARG(rl_stream_ok(B, kp <= 19 ? 4 : 2, view_chk, side), "buffers must be 16-byte aligned and nx a multiple of the vector width");
+  RLZZArgs A;
+  memset(&A, 0, sizeof(A));
+  const int rp = (kp - 1) / 2;
+  if (!compress_map(host_zmap1, dims[0] + 4 * rp, -2 * rp, A.seg1, &A.nseg1) ||
+      !compress_map(host_rmap, dims[0] + 2 * rp, -rp, A.segr, &A.nsegr))
+    return fail(MVF_ERR_UNSUPPORTED, "%s%s", "rl_zz: plane map with more than 8 affine runs");
+  A.in = t1;
+  memcpy(A.kz, B.kz, sizeof(A.kz));
+  A.nz = dims[0]; A.ny = dims[1]; A.nx = dims[2];
+  A.view = view; A.view_u16 = dtype == MVF_U16; A.side = side; A.out = t2_out;
+  return launch_rl_zz(kp, A, as_stream(stream));
+}
+
+extern "C" int mvf_rl_xy_correct(const float* t2, int32_t nplanes, const int32_t dims[3], const mvf_rl_psf* psf,
+                                 const float* weights, float* corr, int first, int last, float* est,
+                                 int64_t est_offset, double* sum_out, void* stream) {
+  RLArgs A;
+  int kp;
+  const int32_t zm_dummy = 0;
+  int rc = fill_rl(A, t2, &zm_dummy, dims, psf, &kp);
+  if (rc) return rc;
+  MVF_CHECK_ARG(weights && corr && nplanes > 0 && nplanes <= 65535, "NULL argument or bad plane count");
+  MVF_CHECK_ARG(!last || est, "est must be given for the last view");
+  MVF_CHECK_ARG(!psf->dense, "the streaming kernels need a separable PSF");
+  A.weights = weights; A.out = corr; A.first = first; A.last = last; A.est = est; A.est_off = est_offset; A.sum = sum_out;
+  MVF_CHECK_ARG(rl_stream_ok(A, kp <= 19 ? 4 : 2, weights, est ? est + est_offset : nullptr),
+                "buffers must be 16-byte aligned and nx a multiple of the vector width");
+  return launch_rl_xy<RL_CORRECT>(kp, A, nplanes, as_stream(stream));
 }

@@ -106,9 +106,29 @@ class FftBlur:
 
 
 def stream_mode():
-    """Separable blurs run as two streaming kernels (x/y passes of all planes, then z pass + epilogue) unless
+    """Separable blurs run as streaming kernels (x/y passes of all planes, z passes along plane maps) unless
     MVF_RL_KERNEL=v1 selects the fused single-kernel variant (also the fallback for rows that are not 16-byte aligned)."""
-    return os.environ.get("MVF_RL_KERNEL", "v3") not in ("v1", "1")
+    return os.environ.get("MVF_RL_KERNEL", "v4") not in ("v1", "1")
+
+
+def zz_mode():
+    """Default streaming schedule (v4): per view  T1 = xy(estimate);  T2 = z(ratio(z(T1)))  in ONE kernel (the ratio
+    volume never reaches HBM);  correction = epilogue(xy(T2)).  MVF_RL_KERNEL=v3 keeps the ratio volume
+    (xy, z + ratio, xy, z + epilogue)."""
+    return os.environ.get("MVF_RL_KERNEL", "v4") in ("v4", "4")
+
+
+def zz_maps_whole(nz, ksz, rp):
+    """Plane maps of mvf_rl_zz for a whole volume: (zmap1 [nz + 4rp], rmap [nz + 2rp], first side plane, side planes).
+    Extended positions outside the volume take their ratio from `side` = the ratio on planes [nz-2-K, nz-2]: the
+    reference's boundary map sends t < 0 to nz-3-K-t (wrap) and t >= nz to 2nz-2-t (reflect)."""
+    zmap1 = ext_index(np.arange(-2 * rp, nz + 2 * rp), nz, ksz).astype(np.int32)
+    t = np.arange(-rp, nz + rp)
+    qa = nz - 2 - ksz
+    q = np.where(t < 0, nz - 3 - ksz - t, 2 * nz - 2 - t)
+    k = np.clip(q - qa, 0, ksz)
+    rmap = np.where((t >= 0) & (t < nz), t, -1 - k).astype(np.int32)
+    return zmap1, rmap, qa, ksz + 1
 
 
 def _vector_aligned(*tensors):
@@ -224,6 +244,14 @@ class RLPlan:
                          _vector_aligned(vw, ww, self.est, self.ratio, self.corr)
                          for sep, ps, vw, ww in zip(self.separable, self.psf_structs, views, weights)]
         self.tmp = torch.empty(self.dims, dtype=torch.float32, device=dev) if any(self.streamed) else None
+        self.zz = zz_mode() and all(self.streamed)
+        if self.zz:   # plane maps of the fused z-ratio-z kernel, side planes for the positions outside the volume
+            self.zz_maps = []
+            for ps, rp in zip(self.psf_structs, self.radii):
+                zmap1, rmap, qa, nside = zz_maps_whole(self.dims[0], int(ps.ksize[0]), rp)
+                self.zz_maps.append((np.ascontiguousarray(zmap1), np.ascontiguousarray(rmap), qa, nside))   # host arrays
+            self.side = torch.empty((max(m[3] for m in self.zz_maps),) + self.dims[1:], dtype=torch.float32, device=dev)
+            self.ratio = None   # never materialised
         # streamed views: (1) the mask (w > 1e-5) of the ratio step is burnt into a copy of the view once, so the ratio
         # pass does not read the weights; (2) views whose PSFs share the in-plane factors (ky, kx) share one x/y pass
         # of the estimate per iteration
@@ -263,6 +291,23 @@ class RLPlan:
                               sums=self.sums[1:])
                 continue
             zm = C.c_void_p(self.zmaps[v].data_ptr())
+            if self.zz:   # side planes, then z + ratio + z in one kernel, then x/y passes + correction epilogue
+                ps = C.byref(self.psf_structs[v])
+                t1 = self.xy_tmps[self.xy_group[v]]
+                zmap1, rmap, qa, nside = self.zz_maps[v]
+                plane = self.dims[1] * self.dims[2]
+                _cabi.check(self.lib.mvf_rl_ratio_z(C.c_void_p(t1.data_ptr()), C.c_void_p(self.zmaps[v].data_ptr() + 4 * qa),
+                                                    _cabi.i32x3((nside,) + self.dims[1:]), ps,
+                                                    C.c_void_p(self.masked[v].data_ptr() + qa * plane * self.masked[v].element_size()),
+                                                    dtype_code(self.views[v]), None, C.c_void_p(self.side.data_ptr()), st))
+                _cabi.check(self.lib.mvf_rl_zz(C.c_void_p(t1.data_ptr()), C.c_void_p(zmap1.ctypes.data), C.c_void_p(rmap.ctypes.data),
+                                               self._dims, ps, C.c_void_p(self.masked[v].data_ptr()), dtype_code(self.views[v]),
+                                               C.c_void_p(self.side.data_ptr()), C.c_void_p(self.tmp.data_ptr()), st))
+                _cabi.check(self.lib.mvf_rl_xy_correct(C.c_void_p(self.tmp.data_ptr()), self.dims[0], self._dims, ps,
+                                                       C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.corr.data_ptr()),
+                                                       1 if v == 0 else 0, 1 if last else 0, C.c_void_p(self.est.data_ptr()), 0,
+                                                       C.c_void_p(self.sums[1:].data_ptr()), st))
+                continue
             if self.streamed[v]:  # x/y passes of every plane into tmp, then z pass + epilogue
                 ps, tmp = C.byref(self.psf_structs[v]), C.c_void_p(self.tmp.data_ptr())
                 _cabi.check(self.lib.mvf_rl_ratio_z(C.c_void_p(self.xy_tmps[self.xy_group[v]].data_ptr()), zm, self._dims, ps,
@@ -373,8 +418,10 @@ class SlabRLPlan:
         self.fft = None
         dense_mode = os.environ.get("MVF_RL_DENSE", "fft")
         rp = None
+        facs = []
         for p in psfs:
             f = None if too_long_for_kernels(p) else factor_psf(p)
+            facs.append(f)
             spec = None
             if f is not None:
                 self.psf_structs.append(make_psf_struct(f))
@@ -398,6 +445,9 @@ class SlabRLPlan:
             rp = r if rp is None else rp
             if r != rp:
                 raise ValueError("PSFs need one common padded size")
+        self.zz = False
+        if zz_mode() and all(f is not None for f in facs) and self._init_zz(views, weights, nz_total, rank, world, kz, rp, group):
+            return
         self.halo = slab.HaloPlan(nz_total, world, rank, kz, rp)
         if self.halo.nzl != nzl:
             raise ValueError("slab height %d does not match the planner's %d" % (nzl, self.halo.nzl))
@@ -441,6 +491,147 @@ class SlabRLPlan:
         self.xy_group, self.xy_tmps = xy_groups(self.psf_structs, self.streamed), []
         for _ in range(max(self.xy_group) + 1 if any(self.streamed) else 0):
             self.xy_tmps.append(torch.empty_like(self.est_pad))
+
+    # ---- v4 schedule on a slab (slab.ZZLayout): one estimate exchange per iteration, no ratio volume ---------------
+    def _init_zz(self, views, weights, nz_total, rank, world, kz, rp, group):
+        """Buffers and plane maps of the v4 schedule; False (nothing allocated) when it does not apply: rows that the
+        vector kernels cannot take, or slabs too thin for 2*rp halo planes - the v3 schedule handles those."""
+        from . import slab
+        import torch.distributed as dist
+        dev = views[0].device
+        nzl, ny, nx = (int(s) for s in views[0].shape)
+        dims = _cabi.i32x3((nzl, ny, nx))
+        if dev.type != "cuda" or not all(bool(self.lib.mvf_rl_stream_supported(dims, C.byref(ps))) for ps in self.psf_structs):
+            return False
+        if not _vector_aligned(*weights):
+            return False
+        try:
+            lay = slab.ZZLayout(nz_total, world, rank, kz, rp)
+        except ValueError:
+            return False
+        if lay.nzl != nzl:
+            raise ValueError("slab height %d does not match the planner's %d" % (nzl, lay.nzl))
+        self.zz, self.layout, self.rp, self.dims = True, lay, rp, (nzl, ny, nx)
+        self.halo = lay            # (.world / .rank / .nzl as for the v3 planner)
+        self.spectra = [None] * self.n
+        self.streamed = [True] * self.n
+        self.symm = None
+        want = os.environ.get("MVF_HALO", "symm")
+        if world > 1 and want == "symm" and dist.is_available() and dist.is_initialized():
+            try:
+                self.symm = slab.SymmetricPull(lay, ny, nx, dev, group)
+            except Exception as e:   # no peer access / no symmetric memory support: point-to-point transfers still work
+                if os.environ.get("MVF_HALO") == "symm":
+                    raise
+                self.symm, self._symm_error = None, repr(e)
+        if self.symm is not None:
+            self.est_pad = self.symm.buf
+            self.comm_stream = torch.cuda.Stream()
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        else:
+            self.est_pad = torch.zeros((lay.height, ny, nx), dtype=torch.float32, device=dev)
+        self.est = self.est_pad[lay.front:lay.front + nzl]
+        self.corr = torch.empty(self.dims, dtype=torch.float32, device=dev)
+        self.t2 = torch.empty(self.dims, dtype=torch.float32, device=dev)
+        self.side = torch.zeros((kz + 1, ny, nx), dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(2, dtype=torch.float64, device=dev)
+        self._vp = (C.c_void_p * self.n)(*[v.data_ptr() for v in views])
+        self._wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in weights])
+        self._dims = dims
+        self._est_off = lay.front * ny * nx
+        # masked views with rp static halo planes (filled from the neighbours once)
+        self.masked_pad = []
+        for vw, ww in zip(views, weights):
+            if vw.dtype == torch.uint16:   # (fill / slice copies via the int16 view: same bits, full operator support)
+                mp = torch.zeros((lay.vheight, ny, nx), dtype=torch.int16, device=dev)
+                mp[rp:rp + nzl] = masked_view(vw, ww).view(torch.int16)
+                mp = mp.view(torch.uint16)
+            else:
+                mp = torch.zeros((lay.vheight, ny, nx), dtype=vw.dtype, device=dev)
+                mp[rp:rp + nzl] = masked_view(vw, ww)
+            self.masked_pad.append(mp)
+        if world > 1 and dist.is_available() and dist.is_initialized():
+            for mp in self.masked_pad:
+                if mp.dtype == torch.uint16:   # (point-to-point backends know int16, not uint16: same bits)
+                    slab.run_transfers_dist(mp.view(torch.int16), lay, "view_transfers", group)
+                else:
+                    slab.run_transfers_dist(mp, lay, "view_transfers", group)
+        self.xy_group = xy_groups(self.psf_structs, self.streamed)
+        self.xy_tmps = [torch.zeros((lay.height, ny, nx), dtype=torch.float32, device=dev) for _ in range(max(self.xy_group) + 1)]
+        self.zmap1 = np.ascontiguousarray(lay.zmap1())   # host arrays: they travel as kernel parameters
+        self.rmap = np.ascontiguousarray(lay.rmap())
+        self.side_jobs = [(torch.from_numpy(zm).to(dev), v0, cnt, k0) for zm, v0, cnt, k0 in lay.side_jobs()]
+        return True
+
+    def _zz_xy_estimate(self, join=None):
+        """x/y passes of the padded estimate, once per group of views with equal in-plane PSF factors.  `join` (halo
+        copies in flight on the side stream): the own planes go first, the halo planes once they have arrived."""
+        lay, st = self.layout, _stream_ptr()
+        pstride = self.dims[1] * self.dims[2] * 4
+        done = set()
+        for v in range(self.n):
+            g = self.xy_group[v]
+            if g in done:
+                continue
+            done.add(g)
+            ps = C.byref(self.psf_structs[v])
+
+            def run(p0, n):
+                if n > 0:
+                    _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est_pad.data_ptr() + p0 * pstride), int(n), self._dims, ps,
+                                                   C.c_void_p(self.xy_tmps[g].data_ptr() + p0 * pstride), st))
+            if join is not None:
+                run(lay.front, lay.nzl)
+                join()
+                join = None
+                run(0, lay.front)
+                run(lay.front + lay.nzl, lay.back)
+            else:
+                run(0, lay.height)
+        if join is not None:
+            join()
+
+    def _zz_view(self, v, before_update=None):
+        """Boundary ratios, then z + ratio + z in one kernel, then x/y passes + correction epilogue of view v
+        (`before_update` runs ahead of the launch that overwrites the estimate)."""
+        st, ps = _stream_ptr(), C.byref(self.psf_structs[v])
+        nzl, ny, nx = self.dims
+        plane = ny * nx
+        t1, mp = self.xy_tmps[self.xy_group[v]], self.masked_pad[v]
+        code = dtype_code(self.views[v])
+        for zm, v0, cnt, k0 in self.side_jobs:
+            _cabi.check(self.lib.mvf_rl_ratio_z(C.c_void_p(t1.data_ptr()), C.c_void_p(zm.data_ptr()), _cabi.i32x3((cnt, ny, nx)), ps,
+                                                C.c_void_p(mp.data_ptr() + v0 * plane * mp.element_size()), code, None,
+                                                C.c_void_p(self.side.data_ptr() + k0 * plane * 4), st))
+        _cabi.check(self.lib.mvf_rl_zz(C.c_void_p(t1.data_ptr()), C.c_void_p(self.zmap1.ctypes.data), C.c_void_p(self.rmap.ctypes.data),
+                                       self._dims, ps, C.c_void_p(mp.data_ptr()), code, C.c_void_p(self.side.data_ptr()),
+                                       C.c_void_p(self.t2.data_ptr()), st))
+        last = v == self.n - 1
+        if last and before_update is not None:
+            before_update()
+        _cabi.check(self.lib.mvf_rl_xy_correct(C.c_void_p(self.t2.data_ptr()), nzl, self._dims, ps,
+                                               C.c_void_p(self.weights[v].data_ptr()), C.c_void_p(self.corr.data_ptr()),
+                                               1 if v == 0 else 0, 1 if last else 0, C.c_void_p(self.est_pad.data_ptr()),
+                                               self._est_off, C.c_void_p(self.sums[1:].data_ptr()), st))
+
+    def iterate_compute(self, join=None, before_update=None):
+        """Everything of a v4 iteration after the estimate halos have been requested / filled."""
+        self.sums[1:].zero_()
+        self._zz_xy_estimate(join)
+        for v in range(self.n):
+            self._zz_view(v, before_update)
+
+    def _iterate_zz_symm(self):
+        main = torch.cuda.current_stream()
+        self.symm.barrier()
+        self._ev_fork.record(main)
+        self.comm_stream.wait_event(self._ev_fork)
+        with torch.cuda.stream(self.comm_stream):
+            self.symm.pull()
+            self._ev_join.record(self.comm_stream)
+        # second barrier: no rank overwrites its estimate (last launch of the iteration) before every peer has pulled the
+        # old planes; the first one orders the pulls after the previous update
+        self.iterate_compute(lambda: main.wait_event(self._ev_join), self.symm.barrier)
 
     def init_estimate(self):
         self.sums.zero_()
@@ -572,6 +763,13 @@ class SlabRLPlan:
 
     def iterate(self):
         from . import slab
+        if self.zz:
+            if self.symm is not None:
+                _graphed(self, self._iterate_zz_symm)
+            else:
+                slab.run_transfers_dist(self.est_pad, self.layout, "est_transfers", self.group)
+                self.iterate_compute()
+            return
         if self.symm is not None:
             _graphed(self, self._iterate_symm)
             return
@@ -608,3 +806,33 @@ class SlabRLPlan:
             i += 1
         self.iterations_run = i + 1
         return self.est
+
+
+def setup_emulated(plans):
+    """Ranks emulated in ONE process (tests on a single GPU): fill the static view halos of the v4 schedule."""
+    from . import slab
+    if plans[0].zz:
+        for v in range(plans[0].n):
+            bufs = [p.masked_pad[v].view(torch.int16) if p.masked_pad[v].dtype == torch.uint16 else p.masked_pad[v] for p in plans]
+            slab.run_transfers_local(bufs, [p.layout for p in plans], "view_transfers")
+
+
+def iterate_emulated(plans):
+    """One RL iteration of all emulated ranks with the same plane movement as the NVLink / NCCL exchanges."""
+    from . import slab
+    if plans[0].zz:
+        slab.run_transfers_local([p.est_pad for p in plans], [p.layout for p in plans], "est_transfers")
+        for p in plans:
+            p.iterate_compute()
+        return
+    for p in plans:
+        p.sums[1:].zero_()
+    slab.exchange_halos_local([p.est_pad for p in plans], [p.halo for p in plans])
+    for p in plans:
+        p.xy_estimate()
+    for v in range(plans[0].n):
+        for p in plans:
+            p.step_ratio(v)
+        slab.exchange_halos_local([p.ratio_pad for p in plans], [p.halo for p in plans])
+        for p in plans:
+            p.step_correct(v)

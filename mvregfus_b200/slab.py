@@ -186,3 +186,212 @@ class SymmetricHalo:
             torch.index_select(self.lower_peer[i], 0, self.lower_idx, out=dst[0:rp])
         if self.upper_peer is not None:
             dst[rp + nzl:rp + nzl + rp].copy_(self.upper_peer[i][rp:2 * rp])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# v4 schedule (rl.zz_mode): per view  T1 = xy(estimate), T2 = z(ratio(z(T1))), correction = epilogue(xy(T2)).
+# The ratio volume is never materialised, so it is never exchanged either: ONE halo exchange per iteration (the
+# estimate, 2*rp planes on each side; rank 0 additionally pulls the planes near the top of the volume that its
+# wrap-around positions refer to), against 1 + V exchanges of the v3 schedule.  The views need rp static halo planes.
+# ---------------------------------------------------------------------------------------------------------------------
+class ZZLayout:
+    """Plane bookkeeping of one rank for the v4 schedule.
+
+    Padded estimate / T1 buffers (same height on every rank): [front: 3rp planes][own: nzl][back: 2rp planes].  The
+    lower halo sits right-aligned in `front`; on rank 0 (world > 1) `front` holds the 3rp planes starting at
+    nz-2-K-rp instead (sources of the wrap-around).  Padded (masked) views: [rp][own][rp]; on rank 0 the front block
+    holds planes [nz-2-K, nz-2-K+rp)."""
+
+    def __init__(self, nz, world, rank, ksize_z, rp):
+        self.nz, self.world, self.rank, self.K, self.rp = int(nz), int(world), int(rank), int(ksize_z), int(rp)
+        self.bounds = slab_bounds(nz, world)
+        self.z0, self.z1 = self.bounds[rank]
+        self.nzl = self.z1 - self.z0
+        self.front, self.back = 3 * self.rp, 2 * self.rp
+        self.height = self.front + self.nzl + self.back
+        self.height_max = self.front + max(b - a for a, b in self.bounds) + self.back
+        self.vheight = self.nzl + 2 * self.rp
+        self.qa = self.nz - 2 - self.K                    # first plane whose ratio the positions outside the volume use
+        self.far0 = self.qa - self.rp
+        if self.nz < self.K + 3:
+            raise ValueError("volume of %d planes is thinner than PSF size + 3" % self.nz)
+        if world > 1:
+            thin = min(b - a for a, b in self.bounds)
+            if thin < 2 * self.rp or self.bounds[-1][1] - self.bounds[-1][0] < self.K + 2 + self.rp or self.far0 < 0:
+                raise ValueError("slabs of %d planes are too thin for halos of %d planes" % (thin, 2 * self.rp))
+
+    # ---- global plane -> local plane ---------------------------------------------------------------------------------
+    def est_local(self, g):
+        """Local plane of global plane(s) g in the padded estimate / T1 buffer, -1 where the rank does not hold it."""
+        g = np.asarray(g)
+        near = (g >= max(0, self.z0 - self.back)) & (g < min(self.nz, self.z1 + self.back)) & (g >= self.z0 - self.back)
+        if self.world > 1 and self.rank == 0:
+            near &= g >= 0
+        loc = np.where(near, self.front + g - self.z0, -1)
+        if self.world > 1 and self.rank == 0:
+            far = (g >= self.far0) & (g < min(self.nz, self.far0 + self.front)) & (loc < 0)
+            loc = np.where(far, g - self.far0, loc)
+        if self.world > 1 and self.rank == self.world - 1:
+            loc = np.where(g >= self.nz, -1, loc)
+        return loc
+
+    def view_local(self, g):
+        g = np.asarray(g)
+        near = (g >= max(0, self.z0 - self.rp)) & (g < min(self.nz, self.z1 + self.rp))
+        loc = np.where(near, self.rp + g - self.z0, -1)
+        if self.world > 1 and self.rank == 0:
+            far = (g >= self.qa) & (g < self.qa + self.rp) & (loc < 0)
+            loc = np.where(far, g - self.qa, loc)
+        return loc
+
+    # ---- plane maps of mvf_rl_zz ------------------------------------------------------------------------------------
+    def _computed(self):
+        """Extended local positions t in [-rp, nzl+rp) whose ratio this rank computes itself (inside the volume)."""
+        t = np.arange(-self.rp, self.nzl + self.rp)
+        g = self.z0 + t
+        return t, (g >= 0) & (g < self.nz)
+
+    def zmap1(self):
+        rp = self.rp
+        s = np.arange(-2 * rp, self.nzl + 2 * rp)
+        loc = self.est_local(_ext(self.z0 + s, self.nz, self.K))
+        t, comp = self._computed()
+        needed = np.zeros(len(s), dtype=bool)
+        for tt in t[comp]:
+            needed[tt + rp:tt + 3 * rp + 1] = True      # s in [t - rp, t + rp]  (index s + 2rp)
+        if np.any(needed & (loc < 0)):
+            raise ValueError("slab layout does not cover the planes the first blur needs")
+        return np.where(loc < 0, self.front, loc).astype(np.int32)
+
+    def rmap(self):
+        t, comp = self._computed()
+        g = self.z0 + t
+        q = np.where(g < 0, self.nz - 3 - self.K - g, 2 * self.nz - 2 - g)     # reference boundary map, unclipped
+        side = -1 - np.clip(q - self.qa, 0, self.K)
+        loc = self.view_local(g)
+        if np.any(comp & (loc < 0)):
+            raise ValueError("slab layout does not cover the view planes the ratio needs")
+        return np.where(comp, loc, side).astype(np.int32)
+
+    def side_jobs(self):
+        """[(zmap [cnt + 2rp], first local view plane, cnt, first side plane)]: ratio planes this rank computes up front
+        with mvf_rl_ratio_z because positions outside the volume repeat them (low edge: wrap, rank 0; top: reflect)."""
+        rp, jobs = self.rp, []
+        ranges = []
+        if self.world == 1:
+            ranges.append((self.qa, self.K + 1))
+        else:
+            if self.rank == 0:
+                ranges.append((self.qa, rp))
+            if self.rank == self.world - 1:
+                ranges.append((self.nz - 1 - rp, rp))
+        for q0, cnt in ranges:
+            tt = np.arange(-rp, cnt + rp)
+            loc = self.est_local(_ext(q0 + tt, self.nz, self.K))
+            if np.any(loc < 0):
+                raise ValueError("slab layout does not cover the planes of the boundary ratios")
+            v0 = self.view_local(np.arange(q0, q0 + cnt))
+            if np.any(v0 < 0) or np.any(np.diff(v0) != 1):
+                raise ValueError("slab layout does not hold the view planes of the boundary ratios")
+            jobs.append((loc.astype(np.int32), int(v0[0]), int(cnt), int(q0 - self.qa)))
+        return jobs
+
+    # ---- plane transfers: (src_rank, first src local plane, count, first dst local plane) --------------------------------
+    def _peer(self, r):
+        return ZZLayout(self.nz, self.world, r, self.K, self.rp)
+
+    def est_transfers(self):
+        """Halo fills of the padded estimate, every iteration (sources are OWN planes of the peers)."""
+        out = []
+        if self.world == 1:
+            return out
+        rp2 = self.back
+        if self.rank > 0:
+            p = self._peer(self.rank - 1)
+            out.append((p.rank, p.front + p.nzl - rp2, rp2, self.front - rp2))
+        if self.rank + 1 < self.world:
+            p = self._peer(self.rank + 1)
+            n = min(rp2, p.nzl)
+            out.append((p.rank, p.front, n, self.front + self.nzl))
+        if self.rank == 0:
+            p = self._peer(self.world - 1)
+            n = min(self.front, self.nz - self.far0)
+            out.append((p.rank, p.front + self.far0 - p.z0, n, 0))
+        return out
+
+    def view_transfers(self):
+        """Static halo fills of the padded (masked) views, once per plan."""
+        out = []
+        if self.world == 1:
+            return out
+        rp = self.rp
+        if self.rank > 0:
+            p = self._peer(self.rank - 1)
+            out.append((p.rank, rp + p.nzl - rp, rp, 0))
+        if self.rank + 1 < self.world:
+            p = self._peer(self.rank + 1)
+            out.append((p.rank, rp, rp, rp + self.nzl))
+        if self.rank == 0:
+            p = self._peer(self.world - 1)
+            out.append((p.rank, rp + self.qa - p.z0, rp, 0))
+        return out
+
+
+def run_transfers_local(bufs, layouts, which):
+    """Plane transfers between the buffers of ranks emulated in ONE process (tests): bufs[r] belongs to rank r."""
+    for r, lay in enumerate(layouts):
+        for src, s0, n, d0 in getattr(lay, which)():
+            bufs[r][d0:d0 + n] = bufs[src][s0:s0 + n]
+
+
+def run_transfers_dist(buf, layout, which, group=None):
+    """The same plane transfers over torch.distributed point-to-point (NCCL on the box, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if layout.world == 1:
+        return
+    staged = buf.is_cuda and dist.get_backend(group) == "gloo"
+    ops, hosts = [], []
+    for r in range(layout.world):      # what the others pull from this rank
+        if r == layout.rank:
+            continue
+        for src, s0, n, d0 in getattr(layout._peer(r), which)():
+            if src == layout.rank:
+                t = buf[s0:s0 + n].contiguous()
+                ops.append(dist.P2POp(dist.isend, t.cpu() if staged else t, r, group=group))
+    for src, s0, n, d0 in getattr(layout, which)():
+        dst = buf[d0:d0 + n]
+        if staged:
+            host = torch.empty(dst.shape, dtype=dst.dtype)
+            hosts.append((host, dst))
+            ops.append(dist.P2POp(dist.irecv, host, src, group=group))
+        else:
+            ops.append(dist.P2POp(dist.irecv, dst, src, group=group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for host, dst in hosts:
+        dst.copy_(host)
+
+
+class SymmetricPull:
+    """Padded estimate volumes of the v4 schedule in torch symmetric memory: every rank copies its halo planes straight
+    out of the peers' buffers over NVLink after a device-side barrier (no NCCL call, CUDA-graph capturable)."""
+
+    def __init__(self, layout, ny, nx, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.layout = layout
+        self.shape = (layout.height_max, int(ny), int(nx))
+        self.store = symm.empty(self.shape, dtype=torch.float32, device=device)
+        self.store.zero_()
+        self.hdl = symm.rendezvous(self.store, group)
+        self.buf = self.store[:layout.height]
+        self.pulls = [(self.hdl.get_buffer(src, self.shape, torch.float32), s0, n, d0)
+                      for src, s0, n, d0 in layout.est_transfers()]
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+    def pull(self):
+        for peer, s0, n, d0 in self.pulls:
+            self.buf[d0:d0 + n].copy_(peer[s0:s0 + n])

@@ -86,16 +86,9 @@ def test_rl_full_size_slab_consistency(cuda):
     whole = rl.RLPlan(views, w, psfs).run(num_iterations=2).clone()
     plans = [rl.SlabRLPlan([v[a:b] for v in views], [x[a:b] for x in w], psfs, shape[0], r, 2)
              for r, (a, b) in enumerate(slab.slab_bounds(shape[0], 2))]
+    rl.setup_emulated(plans)
     for p in plans:
         p.init_estimate()
     for _ in range(2):
-        slab.exchange_halos_local([p.est_pad for p in plans], [p.halo for p in plans])
-        for p in plans:
-            p.xy_estimate()
-        for v in range(V):
-            for p in plans:
-                p.step_ratio(v)
-            slab.exchange_halos_local([p.ratio_pad for p in plans], [p.halo for p in plans])
-            for p in plans:
-                p.step_correct(v)
+        rl.iterate_emulated(plans)
     assert torch.equal(torch.cat([p.est for p in plans], 0), whole)

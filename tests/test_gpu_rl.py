@@ -44,11 +44,13 @@ def test_get_psf_matches_oracle(cuda):
         assert abs(float(got.sum()) - 1) < 1e-5
 
 
+@pytest.mark.parametrize("kernel", ["v1", "v3", "v4"])   # fused single kernel / streaming with ratio volume / z-ratio-z fused (default)
 @pytest.mark.parametrize("nviews,iters", [(2, 4), (4, 10)])
-def test_rl_matches_oracle(cuda, nviews, iters):
+def test_rl_matches_oracle(cuda, nviews, iters, kernel, monkeypatch):
     """north_star: within 1e-3 relative error after N iterations (floor of one grey level)."""
     import torch
     from mvregfus_b200 import fusion, rl, multiview as mv
+    monkeypatch.setenv("MVF_RL_KERNEL", kernel)
     tv, w, params, sp = _axis_case(nviews=nviews)
     ref = O.fuse_LR_with_weights_np(tv, params, sp, num_iterations=iters, sz=3, sxy=1, weights=w, return_float=True)
     psfs = [mv.get_psf(p, sp, 3, 1) for p in params]
@@ -98,11 +100,11 @@ def test_rl_oblique_views_dense_psf(cuda, dense_mode, monkeypatch):
     assert float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0))) <= 1e-3
 
 
-@pytest.mark.parametrize("kernel", ["v1", "v3"])
+@pytest.mark.parametrize("kernel", ["v1", "v3", "v4"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_rl_slab_sharded_equals_whole(cuda, world, kernel, monkeypatch):
-    """z-slab sharded RL (ranks emulated on one GPU, same kernels, same halo plane movement as the NCCL ring)
-    reproduces the single-GPU whole-volume result bit for bit, including the wrap-around low edge."""
+    """z-slab sharded RL (ranks emulated on one GPU, same kernels, same halo plane movement as the NVLink / NCCL
+    exchanges) reproduces the single-GPU whole-volume result bit for bit, including the wrap-around low edge."""
     import torch
     from mvregfus_b200 import fusion, rl, slab, multiview as mv
     monkeypatch.setenv("MVF_RL_KERNEL", kernel)
@@ -114,18 +116,12 @@ def test_rl_slab_sharded_equals_whole(cuda, world, kernel, monkeypatch):
     plans = []
     for r, (z0, z1) in enumerate(slab.slab_bounds(nz, world)):
         plans.append(rl.SlabRLPlan([v[z0:z1].contiguous() for v in dv], [x[z0:z1].contiguous() for x in dw], psfs, nz, r, world))
+    assert all(p.zz == (kernel == "v4") for p in plans)
+    rl.setup_emulated(plans)
     for p in plans:
         p.init_estimate()
     for _ in range(3):
-        slab.exchange_halos_local([p.est_pad for p in plans], [p.halo for p in plans])
-        for p in plans:
-            p.xy_estimate()
-        for v in range(len(dv)):
-            for p in plans:
-                p.step_ratio(v)
-            slab.exchange_halos_local([p.ratio_pad for p in plans], [p.halo for p in plans])
-            for p in plans:
-                p.step_correct(v)
+        rl.iterate_emulated(plans)
     got = torch.cat([p.est for p in plans], 0).cpu().numpy()
     assert np.array_equal(got, whole)
 
@@ -161,7 +157,7 @@ def test_rl_slab_sharded_oblique_fft(cuda):
     assert float(np.max(np.abs(got - whole) / np.maximum(np.abs(whole), 1.0))) <= 1e-3
 
 
-@pytest.mark.parametrize("kernel", ["v1", "v3"])
+@pytest.mark.parametrize("kernel", ["v1", "v3", "v4"])
 def test_rl_float32_views_equal_uint16_views(cuda, kernel, monkeypatch):
     """float32 views holding the same integers take the float operand path of the epilogues: identical estimate."""
     import torch

@@ -68,3 +68,75 @@ def test_ring_halo_exchange_gloo(world, nz, K, rp):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, nz, K, rp, out), nprocs=world, join=True)
     assert all(out[r] == (True, True) for r in range(world)), dict(out)
+
+
+# ---- v4 schedule (slab.ZZLayout): one estimate exchange of 2rp planes per iteration, static view halos -----------------
+def _ext_ref(g, nz, K):
+    g = np.asarray(g)
+    return np.clip(np.where(g < 0, nz - 3 - K - g, np.where(g >= nz, 2 * nz - 2 - g, g)), 0, nz - 1)
+
+
+def _zz_check(lay, est, view, nz, K, rp):
+    """est / view hold GLOBAL plane numbers: every plane the two chained blurs of this rank touch must be the plane the
+    reference's boundary map names for the whole volume."""
+    zm, rm = lay.zmap1(), lay.rmap()
+    for t in range(-rp, lay.nzl + rp):
+        g = lay.z0 + t
+        if 0 <= g < nz:
+            if view[rm[t + rp]] != g:
+                return False
+            for d in range(-rp, rp + 1):
+                if est[zm[t + d + 2 * rp]] != _ext_ref(g + d, nz, K):
+                    return False
+        else:
+            q = nz - 3 - K - g if g < 0 else 2 * nz - 2 - g
+            if -1 - rm[t + rp] != np.clip(q - lay.qa, 0, K):
+                return False
+    for zmj, v0, cnt, k0 in lay.side_jobs():
+        for i in range(cnt):
+            q = lay.qa + k0 + i
+            if view[v0 + i] != q or any(est[zmj[i + d + rp]] != _ext_ref(q + d, nz, K) for d in range(-rp, rp + 1)):
+                return False
+    return True
+
+
+@pytest.mark.parametrize("world,nz,K,rp", [(1, 40, 7, 3), (2, 72, 7, 3), (3, 90, 9, 6), (8, 512, 19, 9)])
+def test_zz_layout_emulated_ranks(world, nz, K, rp):
+    lays = [slab.ZZLayout(nz, world, r, K, rp) for r in range(world)]
+    est = [np.full(l.height, -1) for l in lays]
+    view = [np.full(l.vheight, -1) for l in lays]
+    for l, e, v in zip(lays, est, view):
+        e[l.front:l.front + l.nzl] = np.arange(l.z0, l.z1)
+        v[l.rp:l.rp + l.nzl] = np.arange(l.z0, l.z1)
+    slab.run_transfers_local(est, lays, "est_transfers")
+    slab.run_transfers_local(view, lays, "view_transfers")
+    assert all(_zz_check(l, e, v, nz, K, rp) for l, e, v in zip(lays, est, view))
+
+
+def test_zz_layout_rejects_thin_slabs():
+    with pytest.raises(ValueError):
+        slab.ZZLayout(64, 4, 0, 19, 9)      # 16-plane slabs cannot lend 18 halo planes
+
+
+def _zz_worker(rank, world, port, nz, K, rp, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lay = slab.ZZLayout(nz, world, rank, K, rp)
+    est = torch.full((lay.height, 2, 2), -1.0)
+    est[lay.front:lay.front + lay.nzl] = torch.arange(lay.z0, lay.z1, dtype=torch.float32)[:, None, None]
+    view = torch.full((lay.vheight, 2, 2), -1, dtype=torch.int16)
+    view[rp:rp + lay.nzl] = torch.arange(lay.z0, lay.z1, dtype=torch.int16)[:, None, None]
+    slab.run_transfers_dist(est, lay, "est_transfers")
+    slab.run_transfers_dist(view, lay, "view_transfers")
+    out[rank] = _zz_check(lay, est[:, 0, 0].numpy().astype(np.int64), view[:, 0, 0].numpy().astype(np.int64), nz, K, rp)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nz,K,rp", [(2, 72, 7, 3), (3, 96, 9, 6)])
+def test_zz_transfers_gloo(world, nz, K, rp):
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_zz_worker, args=(world, port, nz, K, rp, out), nprocs=world, join=True)
+    assert all(out[r] is True for r in range(world)), dict(out)

@@ -13,11 +13,19 @@ sc = Rk / 9.0
 k = np.exp(-0.5 * (np.arange(-Rk, Rk + 1) / (6.0 * sc)) ** 2); kz = (k / k.sum()).astype(np.float32)
 k = np.exp(-0.5 * (np.arange(-Rk, Rk + 1) / (2.0 * sc)) ** 2); kxy = (k / k.sum()).astype(np.float32)
 psf = kz[:, None, None] * kxy[None, :, None] * kxy[None, None, :]
+def view_psf(v):   # RL_DISTINCT=1: every view its own factors (no shared x/y passes), as with real registration parameters
+    f = 1.0 + 0.004 * v
+    a = np.exp(-0.5 * (np.arange(-Rk, Rk + 1) / (6.0 * sc * f)) ** 2); b = np.exp(-0.5 * (np.arange(-Rk, Rk + 1) / (2.0 * sc * f)) ** 2)
+    a, b = (a / a.sum()).astype(np.float32), (b / b.sum()).astype(np.float32)
+    return (a[:, None, None] * b[None, :, None] * b[None, None, :]) if v % 2 == 0 else (b[:, None, None] * b[None, :, None] * a[None, None, :])
 if os.environ.get("RL_OBLIQUE"):
     from scipy import ndimage
     psf = ndimage.rotate(psf, 7.0, axes=(0, 2), reshape=False, order=1).astype(np.float32); psf /= psf.sum()
-plan = rl.RLPlan(views, w, [psf] * V)
-plan.init_estimate(); plan.iterate(); torch.cuda.synchronize()
+plan = rl.RLPlan(views, w, [view_psf(v) for v in range(V)] if os.environ.get('RL_DISTINCT') else [psf] * V)
+plan.init_estimate()
+for _ in range(3):   # eager run, graph capture, first replay
+    plan.iterate()
+torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n_it = int(os.environ.get("RL_ITERS", "2"))
 a.record()
