@@ -552,10 +552,8 @@ class SlabRLPlan:
             self.masked_pad.append(mp)
         if world > 1 and dist.is_available() and dist.is_initialized():
             for mp in self.masked_pad:
-                if mp.dtype == torch.uint16:   # (point-to-point backends know int16, not uint16: same bits)
-                    slab.run_transfers_dist(mp.view(torch.int16), lay, "view_transfers", group)
-                else:
-                    slab.run_transfers_dist(mp, lay, "view_transfers", group)
+                # (as bytes: NCCL moves neither uint16 nor int16 tensors)
+                slab.run_transfers_dist(mp.view(torch.uint8) if mp.dtype == torch.uint16 else mp, lay, "view_transfers", group)
         self.xy_group = xy_groups(self.psf_structs, self.streamed)
         self.xy_tmps = [torch.zeros((lay.height, ny, nx), dtype=torch.float32, device=dev) for _ in range(max(self.xy_group) + 1)]
         self.zmap1 = np.ascontiguousarray(lay.zmap1())   # host arrays: they travel as kernel parameters
