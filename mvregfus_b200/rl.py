@@ -563,31 +563,32 @@ class SlabRLPlan:
 
     def _zz_xy_estimate(self, join=None):
         """x/y passes of the padded estimate, once per group of views with equal in-plane PSF factors.  `join` (halo
-        copies in flight on the side stream): the own planes go first, the halo planes once they have arrived."""
+        copies in flight on the side stream): the own planes of every group go first, the halo planes once they have
+        arrived.  Ranks other than 0 use only the upper 2rp planes of the front block."""
         lay, st = self.layout, _stream_ptr()
         pstride = self.dims[1] * self.dims[2] * 4
-        done = set()
+        lo = 0 if (lay.rank == 0 or lay.world == 1) else lay.front - lay.back
+        nback = lay.back if lay.rank + 1 < lay.world else 0      # (the last rank reflects into its own planes)
+        groups, seen = [], set()
         for v in range(self.n):
-            g = self.xy_group[v]
-            if g in done:
-                continue
-            done.add(g)
-            ps = C.byref(self.psf_structs[v])
+            if self.xy_group[v] not in seen:
+                seen.add(self.xy_group[v])
+                groups.append((self.xy_group[v], C.byref(self.psf_structs[v])))
 
-            def run(p0, n):
-                if n > 0:
-                    _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est_pad.data_ptr() + p0 * pstride), int(n), self._dims, ps,
-                                                   C.c_void_p(self.xy_tmps[g].data_ptr() + p0 * pstride), st))
-            if join is not None:
-                run(lay.front, lay.nzl)
-                join()
-                join = None
-                run(0, lay.front)
-                run(lay.front + lay.nzl, lay.back)
-            else:
-                run(0, lay.height)
-        if join is not None:
-            join()
+        def run(g, ps, p0, n):
+            if n > 0:
+                _cabi.check(self.lib.mvf_rl_xy(C.c_void_p(self.est_pad.data_ptr() + p0 * pstride), int(n), self._dims, ps,
+                                               C.c_void_p(self.xy_tmps[g].data_ptr() + p0 * pstride), st))
+        if join is None:
+            for g, ps in groups:
+                run(g, ps, lo, lay.front + lay.nzl + nback - lo)
+            return
+        for g, ps in groups:
+            run(g, ps, lay.front, lay.nzl)
+        join()
+        for g, ps in groups:
+            run(g, ps, lo, lay.front - lo)
+            run(g, ps, lay.front + lay.nzl, nback)
 
     def _zz_view(self, v, before_update=None):
         """Boundary ratios, then z + ratio + z in one kernel, then x/y passes + correction epilogue of view v
