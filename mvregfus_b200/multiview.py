@@ -8,6 +8,8 @@ CUDA kernels of libmvregfus_b200 through the C-ABI.  All functions are plain Pyt
 Host arrays in, host arrays out (the reference's contract); the device-resident API that avoids the
 PCIe round trip per call is ``mvregfus_b200.fusion`` / ``mvregfus_b200.pipeline``.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -209,8 +211,19 @@ def get_weights_simple(orig_stack_propertiess, params, stack_properties):
     """Sigmoid-border blending weights of every view on the target grid, normalised over views
     (mv:3469-3633).  Returns a list of V float32 arrays like the reference."""
     dims = [int(s) for s in stack_properties["size"]]
-    vs = fusion.build_viewset(None, orig_stack_propertiess, params, stack_properties, weights="blending")
-    w = fusion.to_host(fusion.blend_weights(vs, dims, (0, 0, 0), normalise=True))
+    if len(params) <= 8:
+        vs = fusion.build_viewset(None, orig_stack_propertiess, params, stack_properties, weights="blending")
+        w = fusion.to_host(fusion.blend_weights(vs, dims, (0, 0, 0), normalise=True))
+    else:   # more than 8 views: raw weights per group of 8, then the reference's normalisation (sum in view order, 0 -> 1)
+        raw = []
+        for i0 in range(0, len(params), 8):
+            vs = fusion.build_viewset(None, orig_stack_propertiess[i0:i0 + 8], params[i0:i0 + 8], stack_properties, weights="blending")
+            raw.extend(fusion.blend_weights(vs, dims, (0, 0, 0), normalise=False).unbind(0))
+        wsum = torch.zeros_like(raw[0])
+        for r in raw:
+            wsum += r
+        wsum[wsum == 0] = 1
+        w = fusion.to_host(torch.stack([r / wsum for r in raw]))
     return [ImageArray(w[i], origin=stack_properties["origin"], spacing=stack_properties["spacing"])
             for i in range(len(params))]
 
@@ -224,11 +237,22 @@ def fuse_views_weights(views, params, stack_properties, weights=None, views_in_t
                  for iview, view in enumerate(views)]
     dviews = [fusion.to_device(v) for v in views]
     dweights = [fusion.to_device(np.asarray(w, dtype=np.float32)) for w in weights] if weights is not None else None
-    out = None
-    for i0 in range(0, len(dviews), 8):  # > 8 views: the uint16 accumulation is associative modulo 2^16 only
-        if i0:                           # for uint16 views; keep the reference contract for the common case
-            raise Exception("fuse_views_weights: more than 8 views are not supported by one fused pass")
-        out = fusion.fuse_weighted(dviews[i0:i0 + 8], dweights[i0:i0 + 8] if dweights is not None else None)
+    if len(dviews) <= 8:
+        out = fusion.fuse_weighted(dviews, dweights)
+    elif dweights is None:
+        # mean of more than 8 views: float64 sum on the device, clipped and truncated like np.mean(...) -> astype(uint16)
+        acc = torch.zeros(dviews[0].shape, dtype=torch.float64, device=dviews[0].device)
+        for v in dviews:
+            acc += v.to(torch.int32).to(torch.float64) if v.dtype == torch.uint16 else v.to(torch.float64)
+        out = (acc / len(dviews)).clamp_(0, 65535).to(torch.int32).to(torch.uint16)
+    else:
+        # more than 8 views: one fused pass per group of 8.  Every term uint16(w_v * I_v) is a non-negative integer, so
+        # the groups add exactly: uint16 views accumulate modulo 2^16 (the reference's uint16 `f`), float32 views saturate
+        # at 65535 (a group that saturates means the total does, too).
+        acc = torch.zeros(dviews[0].shape, dtype=torch.int32, device=dviews[0].device)
+        for i0 in range(0, len(dviews), 8):
+            acc += fusion.fuse_weighted(dviews[i0:i0 + 8], dweights[i0:i0 + 8]).to(torch.int32)
+        out = (acc & 0xFFFF if dviews[0].dtype == torch.uint16 else acc.clamp_(max=65535)).to(torch.uint16)
     return ImageArray(fusion.to_host(out), spacing=stack_properties["spacing"], origin=stack_properties["origin"])
 
 
@@ -397,7 +421,7 @@ def fuse_block(tviews_block, weights, params, stack_properties, orig_stack_prope
             kwargs['orig_stack_propertiess'] = view_frames
     tviews = [ImageArray(t, spacing=frame['spacing'], origin=frame['origin']) for t in block_views]
     blending = weights is None and weights_func == get_weights_simple
-    if blending and fusion_func in (fuse_views_weights, fuse_LR_with_weights_np):
+    if blending and fusion_func in (fuse_views_weights, fuse_LR_with_weights_np) and len(keep) <= 8:
         # device-resident: same decisions, but the block's weights never travel over PCIe
         return _fuse_block_device(block_views, params, view_frames, frame, fusion_func, fusion_kwargs)
     if blending:
@@ -472,6 +496,50 @@ def _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_properties
     return fusion.to_host(fused)
 
 
+def _fuse_blocks_on_device(tviews, params, stack_properties, orig_stack_propertiess, depth, weights_func, fusion_func,
+                           weights_kwargs, fusion_kwargs):
+    """The block loop of fuse_blockwise with everything resident in HBM (mvregfus_b200.pipeline.fuse_blocks_device): any
+    overlap, blending or DCT weights, weighted average or Richardson-Lucy.  None if the request is outside that set
+    (custom weight / fusion functions, more than 8 views, mixed dtypes): the host loop below handles it."""
+    from . import dct, pipeline
+    if fusion_func not in (fuse_views_weights, fuse_LR_with_weights_np) or weights_func not in (get_weights_simple, get_weights_dct):
+        return None
+    if len(tviews) > 8 or len({np.dtype(t.dtype) for t in tviews}) != 1 or np.dtype(tviews[0].dtype) not in (np.dtype(np.uint16), np.dtype(np.float32)):
+        return None
+    if weights_func == get_weights_simple and weights_kwargs:
+        return None
+    extra = set(fusion_kwargs) - ({'num_iterations', 'sz', 'sxy', 'tol'} if fusion_func == fuse_LR_with_weights_np else set())
+    if extra:
+        return None
+    dviews = []
+    for t in tviews:
+        if isinstance(t, LazyTransformedView) and t._value is None:   # resampled on the device, never materialised on the host
+            matrix, offset = index_space_affine(t.p, t.stack.spacing, t.stack.origin, t.spacing, t.origin)
+            dviews.append(fusion.affine_resample(fusion.to_device(t.stack), matrix, offset, list(t.shape), (0, 0, 0), rule="scipy"))
+        else:
+            dviews.append(fusion.to_device(np.asarray(t)))
+    chunks = None
+    if weights_func == get_weights_dct:
+        shape = dviews[0].shape
+        exp = [int(-(-s // dct.CHUNK)) * dct.CHUNK for s in shape]
+        padded = []
+        for d in dviews:
+            if list(shape) == exp:
+                padded.append(d)
+                continue
+            p = torch.zeros(exp, dtype=torch.int16 if d.dtype == torch.uint16 else d.dtype, device=d.device)
+            p[:shape[0], :shape[1], :shape[2]] = d.view(torch.int16) if d.dtype == torch.uint16 else d
+            padded.append(p.view(torch.uint16) if d.dtype == torch.uint16 else p)
+        opts = dict(weights_kwargs)
+        chunks, _ = dct.weights_dct_chunks(padded, params, orig_stack_propertiess, stack_properties, depth=depth,
+                                           max_kernel=opts.get('max_kernel'),
+                                           how_many_best_views=opts.get('how_many_best_views', 2),
+                                           cumulative_weight_best_views=opts.get('cumulative_weight_best_views', 0.9))
+    fused = pipeline.fuse_blocks_device(dviews, params, stack_properties, orig_stack_propertiess, depth,
+                                        'wavg' if fusion_func == fuse_views_weights else 'rl', fusion_kwargs, chunks)
+    return fusion.to_host(fused)
+
+
 def fuse_blockwise_arrays(tviews, params, stack_properties, orig_stack_propertiess, fusion_block_overlap=None,
                           weights_func=None, fusion_func=None, weights_kwargs=None, fusion_kwargs=None):
     """The block loop of fuse_blockwise (mv:3709-3780) on in-memory transformed views: 128^3 chunks with a
@@ -485,6 +553,11 @@ def fuse_blockwise_arrays(tviews, params, stack_properties, orig_stack_propertie
     if depth == 0 and weights_func == get_weights_simple and fusion_func == fuse_views_weights and not weights_kwargs \
             and not fusion_kwargs:
         fused = _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_propertiess)
+        if fused is not None:
+            return fused
+    if os.environ.get("MVF_BLOCKWISE", "device") != "host":
+        fused = _fuse_blocks_on_device(tviews, params, stack_properties, orig_stack_propertiess, depth, weights_func,
+                                       fusion_func, weights_kwargs, fusion_kwargs)
         if fused is not None:
             return fused
     orig_shape = np.array(tviews[0].shape)

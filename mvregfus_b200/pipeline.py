@@ -66,3 +66,126 @@ def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_propertie
     _cabi.check(lib.mvf_fuse_blend_chunked(vs.n, vs.structs, C.c_void_p(out.data_ptr()), _cabi.i32x3(dims),
                                            _cabi.i32x3((0, 0, 0)), C.c_void_p(info.data_ptr()), chunk, _cabi.i32x3(nch), st))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Device-resident block loop for every weight / fusion mode of fuse_blockwise (mv:3709-3780, 3817-3916): transformed
+# views, overlap blocks (halo + reflection at the volume faces), per-block decisions, weights, weighted average or
+# Richardson-Lucy and the trimmed result all stay in HBM; the host sees two small flag arrays and, at the end, the fused
+# volume.  Blocks remain independent problems with the reference's block-local frames and boundary handling, so the
+# result is the block loop's, not a whole-volume fusion.
+# ---------------------------------------------------------------------------------------------------------------------
+def _bits(t):
+    """uint16 tensors as int16 bit patterns (index / pad / copy operators exist for int16, values are only moved)."""
+    return t.view(torch.int16) if t.dtype == torch.uint16 else t
+
+
+def overlap_block_device(sources, loc, depth, chunk=CHUNK):
+    """(V, chunk+2d, ...) block of every source with a `depth` halo: neighbouring voxels inside the volume, reflection
+    (no edge repeat) at its faces, zeros for chunks beyond it - overlap_from_sources, mv:3662-3707."""
+    extent = np.array(sources[0].shape)
+    first = np.array(loc) * chunk
+    edge = chunk + 2 * depth
+    block = torch.zeros((len(sources), edge, edge, edge), dtype=_bits(sources[0]).dtype, device=sources[0].device)
+    if np.any(first >= extent):
+        return block
+    last = first + chunk
+    lo = [int(max(0, a - depth)) for a in first]
+    hi = [int(min(n, b + depth)) for b, n in zip(last, extent)]
+    missing = [(depth if a == 0 else 0, int(max(0, depth - (n - b)))) for a, b, n in zip(first, last, extent)]
+    idx = []
+    for d in range(3):   # np.pad(mode='reflect') of the window as an index list per axis
+        n = hi[d] - lo[d]
+        before, after = missing[d]
+        if n > 1:
+            pos = np.arange(-before, n + after)
+            period = 2 * (n - 1)
+            pos = np.abs(pos) % period
+            pos = np.where(pos >= n, period - pos, pos)
+        else:
+            pos = np.zeros(n + before + after, dtype=np.int64)
+        idx.append(torch.as_tensor(pos + lo[d], device=sources[0].device, dtype=torch.long))
+    sz = [len(i) for i in idx]
+    for v, src in enumerate(sources):
+        part = _bits(src).index_select(0, idx[0]).index_select(1, idx[1]).index_select(2, idx[2])
+        block[v, :sz[0], :sz[1], :sz[2]] = part
+    return block
+
+
+def fuse_blocks_device(tviews, params, stack_properties, orig_stack_propertiess, depth, mode, fusion_kwargs=None,
+                       weight_chunks=None, chunk=CHUNK):
+    """tviews: V CUDA tensors (transformed views, one dtype).  mode: 'wavg' | 'rl'.  weight_chunks: None (blending
+    weights of every block frame) or {chunk location: (V, chunk+2d, ...) float32 CUDA tensor} (DCT mode).  Returns the
+    fused CUDA tensor in the dtype of the views, cropped to their shape - what the reference's block loop assembles."""
+    from . import multiview as mv, rl
+    opt = dict(fusion_kwargs or {})
+    dev, vdtype = tviews[0].device, tviews[0].dtype
+    V = len(tviews)
+    shape = [int(s) for s in tviews[0].shape]
+    nch = [-(-s // chunk) for s in shape]
+    locs = list(np.ndindex(*nch))
+    edge = chunk + 2 * depth
+    out = torch.zeros([n * chunk for n in nch], dtype=_bits(tviews[0]).dtype, device=dev)
+    params = np.asarray(params, dtype=np.float64)
+
+    def frame_of(loc):
+        shift = np.array(loc, dtype=np.float64) * chunk - depth
+        return {"size": np.array([edge] * 3), "spacing": np.asarray(stack_properties["spacing"], dtype=np.float64),
+                "origin": np.asarray(stack_properties["origin"], dtype=np.float64) + shift * np.asarray(stack_properties["spacing"])}
+
+    def put(loc, block):   # trimmed block -> its chunk of the output
+        b = block[depth:edge - depth, depth:edge - depth, depth:edge - depth] if depth > 0 else block
+        out[loc[0] * chunk:(loc[0] + 1) * chunk, loc[1] * chunk:(loc[1] + 1) * chunk, loc[2] * chunk:(loc[2] + 1) * chunk] = b
+
+    def as_view_dtype(u16):   # fused uint16 values in the dtype the block loop assembles
+        return u16.view(torch.int16) if vdtype == torch.uint16 else u16.to(torch.int32).to(vdtype)
+
+    # pass 1: which views have signal in which block (one host sync for all blocks)
+    live = torch.stack([(overlap_block_device(tviews, loc, depth, chunk) != 0).flatten(1).any(1) for loc in locs]).cpu().numpy()
+    # pass 2: which of those views have a weight in the block
+    wlive, cand = {}, [i for i, loc in enumerate(locs) if live[i].sum() >= 2]
+    flags = []
+    for i in cand:
+        keep = np.where(live[i])[0]
+        if weight_chunks is None:
+            vs = fusion.build_viewset(None, [orig_stack_propertiess[k] for k in keep], params[keep], frame_of(locs[i]), weights="blending")
+            w = fusion.blend_weights(vs, [edge] * 3, (0, 0, 0), normalise=True)
+        else:
+            w = weight_chunks[locs[i]][torch.as_tensor(keep, device=dev)]
+        f = torch.zeros(V, dtype=torch.bool, device=dev)
+        f[:len(keep)] = w.flatten(1).amax(1) > 0
+        flags.append(f)
+    if flags:
+        fl = torch.stack(flags).cpu().numpy()
+        for n, i in enumerate(cand):
+            wlive[i] = fl[n][:int(live[i].sum())]
+    # pass 3: raw copies and fusions
+    for i, loc in enumerate(locs):
+        keep = np.where(live[i])[0]
+        blk = overlap_block_device(tviews, loc, depth, chunk)
+        if len(keep) < 2:
+            put(loc, blk[keep[0] if len(keep) else 0])
+            continue
+        weighted = np.where(wlive[i])[0]
+        if len(weighted) < 2:
+            put(loc, blk[keep[weighted[0] if len(weighted) else 0]])
+            continue
+        frame = frame_of(loc)
+        if weight_chunks is None:
+            vs = fusion.build_viewset(None, [orig_stack_propertiess[k] for k in keep], params[keep], frame, weights="blending")
+            w = fusion.blend_weights(vs, [edge] * 3, (0, 0, 0), normalise=True)
+            dweights = list(w.unbind(0))
+        else:
+            dweights = [weight_chunks[loc][k].contiguous() for k in keep]
+        dviews = [(blk[k].view(torch.uint16) if vdtype == torch.uint16 else blk[k]).contiguous() for k in keep]
+        if mode == "wavg":
+            fused = fusion.fuse_weighted(dviews, dweights)
+        else:
+            psfs = [mv.get_psf(params[k], frame, opt.get("sz", 4), opt.get("sxy", 0.5)) for k in keep]
+            est = rl.RLPlan(dviews, dweights, psfs).run(num_iterations=opt.get("num_iterations", 25), tol=opt.get("tol", 5e-5))
+            fused = est.to(torch.int32).to(torch.uint16)
+        put(loc, as_view_dtype(fused))
+    res = out[:shape[0], :shape[1], :shape[2]]
+    res = res.contiguous()
+    return res.view(torch.uint16) if vdtype == torch.uint16 else res
+

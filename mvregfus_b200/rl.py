@@ -261,10 +261,7 @@ class RLPlan:
             self.xy_tmps.append(torch.empty(self.dims, dtype=torch.float32, device=dev))
 
     def init_estimate(self):
-        self.sums.zero_()
-        _cabi.check(self.lib.mvf_rl_init_estimate(self.n, self._vp, dtype_code(self.views[0]), self._wp,
-                                                  C.c_void_p(self.est.data_ptr()), self.est.numel(),
-                                                  C.c_void_p(self.sums.data_ptr()), _stream_ptr()))
+        _init_estimate(self)
 
     def iterate(self):
         """One RL iteration; sum(estimate) lands in self.sums[1].  After the first (eager) call the launches of an
@@ -348,6 +345,30 @@ class RLPlan:
             i += 1
         self.iterations_run = i + 1
         return self.est
+
+
+def _init_estimate(plan):
+    """estimate = sum_v w_v * I_v and its sum (mv:5640-5645); more than MVF_MAX_VIEWS views go through the kernel in
+    groups whose partial estimates are added."""
+    plan.sums.zero_()
+    code, est = dtype_code(plan.views[0]), plan.est
+    cap = 8
+    if plan.n <= cap:
+        _cabi.check(plan.lib.mvf_rl_init_estimate(plan.n, plan._vp, code, plan._wp, C.c_void_p(est.data_ptr()), est.numel(),
+                                                  C.c_void_p(plan.sums.data_ptr()), _stream_ptr()))
+        return
+    part = torch.empty(tuple(est.shape), dtype=torch.float32, device=est.device)
+    for i0 in range(0, plan.n, cap):
+        n = min(cap, plan.n - i0)
+        vp = (C.c_void_p * n)(*[v.data_ptr() for v in plan.views[i0:i0 + n]])
+        wp = (C.c_void_p * n)(*[w.data_ptr() for w in plan.weights[i0:i0 + n]])
+        dst = est if i0 == 0 else part
+        if i0 == 0 and not est.is_contiguous():
+            raise ValueError("estimate buffer must be contiguous")
+        _cabi.check(plan.lib.mvf_rl_init_estimate(n, vp, code, wp, C.c_void_p(dst.data_ptr()), dst.numel(), None, _stream_ptr()))
+        if i0:
+            est += part
+    plan.sums[0] = est.sum(dtype=torch.float64)
 
 
 def _graphed(plan, eager):
@@ -633,10 +654,7 @@ class SlabRLPlan:
         self.iterate_compute(lambda: main.wait_event(self._ev_join), self.symm.barrier)
 
     def init_estimate(self):
-        self.sums.zero_()
-        _cabi.check(self.lib.mvf_rl_init_estimate(self.n, self._vp, dtype_code(self.views[0]), self._wp,
-                                                  C.c_void_p(self.est.data_ptr()), self.est.numel(),
-                                                  C.c_void_p(self.sums.data_ptr()), _stream_ptr()))
+        _init_estimate(self)
 
     def _xy_planes(self, src_pad, v, pending=(), dst=None):
         """x/y passes of src_pad into dst (default tmp_pad).  With a halo exchange in flight (`pending`) the own planes

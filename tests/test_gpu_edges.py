@@ -97,3 +97,32 @@ def test_mixed_dtypes_in_one_fusion_call_are_refused(cuda):
     vs = fusion.build_viewset(dv, props, params, sp, weights="blending")
     with pytest.raises(_cabi.MvfError):
         fusion.fuse_blend(vs, [int(s) for s in sp["size"]])
+
+
+def test_more_than_eight_views_weighted_fusion_and_rl(cuda):
+    """The reference accepts any number of views (mv:4879-4914, 5545-5749): beyond the 8 views of one fused pass the
+    drop-in entry points work in groups - weights, weighted sum (uint16 wrap / float32 clip) and the RL start estimate."""
+    import numpy as np
+    from mvregfus_b200 import multiview as mv, synthetic
+    from oracle import mvregfus_oracle as O
+    shape, V = (40, 36, 48), 10
+    views, params, props = synthetic.make_views(shape, V, dtype=np.uint16, seed=7)
+    sp = {"size": np.array(shape), "spacing": np.ones(3), "origin": np.zeros(3)}
+    w = mv.get_weights_simple(props, params, sp)
+    wr = O.get_weights_simple(props, params, sp)
+    assert len(w) == V and max(float(np.abs(np.asarray(a) - np.asarray(b)).max()) for a, b in zip(w, wr)) <= 2e-6
+    from mvregfus_b200.image_array import ImageArray
+    tv = [np.asarray(O.transform_stack_dask_numpy(ImageArray(v, spacing=q["spacing"], origin=q["origin"]), p, sp))
+          for v, p, q in zip(views, params, props)]
+    for cast in (np.uint16, np.float32):
+        tvc = [t.astype(cast) * (9 if cast == np.uint16 else 1) for t in tv]      # x9: the uint16 sum wraps modulo 2^16
+        big = [np.full(shape, 0.9, dtype=np.float32) for _ in range(V)]
+        got = np.asarray(mv.fuse_views_weights(tvc, params, sp, weights=big))
+        ref = np.asarray(O.fuse_views_weights(tvc, params, sp, weights=big))
+        assert np.array_equal(got, ref)
+    got = np.asarray(mv.fuse_views_weights(tv, params, sp, weights=None))
+    ref = np.asarray(O.fuse_views_weights(tv, params, sp, weights=None))
+    assert np.max(np.abs(got.astype(np.int64) - ref.astype(np.int64))) <= 1
+    est = np.asarray(mv.fuse_LR_with_weights_np(tv, params, sp, num_iterations=2, sz=3, sxy=1, weights=wr))
+    ref = np.asarray(O.fuse_LR_with_weights_np(tv, params, sp, num_iterations=2, sz=3, sxy=1, weights=wr))
+    assert np.max(np.abs(est.astype(np.int64) - ref.astype(np.int64))) <= 1
