@@ -216,39 +216,71 @@ __global__ void __launch_bounds__(RLE_NT) rl_xy_edge_kernel(const __grid_constan
   float* __restrict__ dst = A.out + (size_t)blockIdx.z * plane;
   const float* __restrict__ wts = MODE == RL_CORRECT ? A.weights + (size_t)blockIdx.z * plane : nullptr;
   float* __restrict__ est = (MODE == RL_CORRECT && A.est) ? A.est + A.est_off + (size_t)blockIdx.z * plane : nullptr;
-  for (int e = threadIdx.x; e < nrows * W; e += RLE_NT) {
-    const int r = e / W, i = e - r * W;
-    strip[e] = __ldg(src + (size_t)ext_index(yo0 - R + r, A.ny, A.ksz_y) * A.nx + ext_index(xs + i - R, A.nx, A.ksz_x));
+  // Thread <-> (column, row group): the column part of every index is computed once per thread, rows advance by a
+  // constant - no division and one index map per element (the kernel was bound by its integer arithmetic).
+  // Staging: fixed trip counts, every load of a thread issued before the first store (one memory round trip per CTA).
+  constexpr int WP = W <= 32 ? 32 : 64, RPW = RLE_NT / WP;          // threads per strip row, rows per pass
+  constexpr int NLOAD = (RLE_ROWS + 2 * R + RPW - 1) / RPW;
+  {
+    const int i = threadIdx.x % WP, r0 = threadIdx.x / WP;
+    const int colx = ext_index(xs + i - R, A.nx, A.ksz_x);
+    float v[NLOAD];
+#pragma unroll
+    for (int k = 0; k < NLOAD; ++k) {
+      const int r = r0 + k * RPW;
+      v[k] = 0.f;
+      if (i < W && r < nrows) v[k] = __ldg(src + (size_t)ext_index(yo0 - R + r, A.ny, A.ksz_y) * A.nx + colx);
+    }
+#pragma unroll
+    for (int k = 0; k < NLOAD; ++k) {
+      const int r = r0 + k * RPW;
+      if (i < W && r < nrows) strip[r * W + i] = v[k];
+    }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < nrows * LEAD; e += RLE_NT) {   // out[x] = sum_j k[j] in[x + R - j]
-    const int r = e / LEAD, c = e - r * LEAD;
-    const float* __restrict__ w = strip + r * W + c + 2 * R;
-    float o = 0.f;
+  constexpr int LP = LEAD <= 16 ? 16 : 32, RPL = RLE_NT / LP;       // threads per output row, rows per pass
+  const int c = threadIdx.x % LP, rl0 = threadIdx.x / LP;
+  if (c < LEAD) {
+    for (int r = rl0; r < nrows; r += RPL) {   // out[x] = sum_j k[j] in[x + R - j]
+      const float* __restrict__ w = strip + r * W + c + 2 * R;
+      float o = 0.f;
 #pragma unroll
-    for (int j = 0; j < K; ++j) o = fmaf(A.kx[j], w[-j], o);
-    xres[e] = o;
+      for (int j = 0; j < K; ++j) o = fmaf(A.kx[j], w[-j], o);
+      xres[r * LEAD + c] = o;
+    }
   }
   __syncthreads();
   double local_sum = 0.0;
-  for (int e = threadIdx.x; e < (yo1 - yo0) * LEAD; e += RLE_NT) {
-    const int r = e / LEAD, c = e - r * LEAD;   // output row yo0 + r: x-pass rows r .. r + 2R of the strip
-    const size_t o1 = (size_t)(yo0 + r) * A.nx + xs + c;
-    float eW = 0.f, eC = 0.f, eI = 0.f;
-    if (MODE == RL_CORRECT) {
-      eW = __ldg(wts + o1);
-      if (!A.first) eC = dst[o1];
-      if (A.last) eI = est[o1];
+  constexpr int NOUT = (RLE_ROWS + RPL - 1) / RPL;
+  const int nout = yo1 - yo0;
+  float eW[NOUT], eC[NOUT], eI[NOUT];
+  if (MODE == RL_CORRECT) {   // epilogue operands of all outputs of the thread in flight before the y passes
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      const int r = rl0 + k * RPL;
+      eW[k] = eC[k] = eI[k] = 0.f;
+      if (c < LEAD && r < nout) {
+        const size_t o1 = (size_t)(yo0 + r) * A.nx + xs + c;
+        eW[k] = __ldg(wts + o1);
+        if (!A.first) eC[k] = dst[o1];
+        if (A.last) eI[k] = est[o1];
+      }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) {
+    const int r = rl0 + k * RPL;                 // output row yo0 + r: x-pass rows r .. r + 2R of the strip
+    if (c >= LEAD || r >= nout) continue;
+    const size_t o1 = (size_t)(yo0 + r) * A.nx + xs + c;
     const float* __restrict__ col = xres + r * LEAD + c;
     float acc = A.ky[K - 1] * col[0];            // oldest row first, as the shift register does
 #pragma unroll
     for (int j = K - 2; j >= 0; --j) acc = fmaf(A.ky[j], col[(K - 1 - j) * LEAD], acc);
     if (MODE == RL_CORRECT) {
-      const float ow = fmaxf(acc, 0.f) * eW;
-      const float corr = A.first ? ow : eC + ow;
+      const float ow = fmaxf(acc, 0.f) * eW[k];
+      const float corr = A.first ? ow : eC[k] + ow;
       if (A.last) {
-        const float rr = fminf(fmaxf(eI * corr, 0.f), 65535.f);
+        const float rr = fminf(fmaxf(eI[k] * corr, 0.f), 65535.f);
         est[o1] = rr;
         local_sum += (double)rr;
       } else {
