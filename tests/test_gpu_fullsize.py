@@ -37,7 +37,7 @@ def test_config2_full_size_against_oracle_subboxes(cuda, dtype):
     maps = [O.index_space_affine(params[v], props[v]["spacing"], props[v]["origin"], sp["spacing"], sp["origin"]) for v in range(4)]
     rng = np.random.default_rng(5)
     box = 40
-    worst_f, worst_i, frac = 0.0, 0, 0.0
+    worst_f, worst_i, frac, frac_f = 0.0, 0, 0.0, 0.0
     for corner in ([60, 70, 80], [230, 240, 250], [dims[0] - box - 6, 200, dims[2] - box - 9], list(rng.integers(50, 400, 3))):
         off = np.array(corner)
         tv = [O.transform_chunk(host_views[v], maps[v][0], maps[v][1], off, [box] * 3) for v in range(4)]
@@ -47,12 +47,20 @@ def test_config2_full_size_against_oracle_subboxes(cuda, dtype):
         sl = tuple(slice(int(o), int(o) + box) for o in off)
         d = np.abs(out[sl].astype(np.int64) - ref.astype(np.int64))
         worst_i, frac = max(worst_i, int(d.max())), max(frac, float(np.mean(d > 0)))
+        ref_f = O.fuse_views_weights_float(tv, w)
+        rel = np.abs(outf[sl] - ref_f) / np.maximum(np.abs(ref_f), 1.0)
         if dtype == np.float32:
-            ref_f = O.fuse_views_weights_float(tv, w)
-            worst_f = max(worst_f, float(np.max(np.abs(outf[sl] - ref_f) / np.maximum(np.abs(ref_f), 1.0))))
-    assert worst_i <= 4 and frac <= 8e-3, (worst_i, frac)
+            worst_f = max(worst_f, float(rel.max()))
+        else:   # uint16 views: every resampled voxel-view is rounded to an integer first (scipy's uint16 output); a value
+            # within float32 rounding of a .5 boundary may land on the other integer, i.e. the sum moves by w_v <= 1
+            worst_f = max(worst_f, float(np.abs(outf[sl] - ref_f).max()))
+            frac_f = max(frac_f, float(np.mean(rel > 1e-5)))
+    # measured on B200 (profiles/r02/parity_report_fullsize.txt): max |d| 1 LSB on 2.4e-5 of the voxels
+    assert worst_i <= 2 and frac <= 5e-4, (worst_i, frac)
     if dtype == np.float32:
         assert worst_f <= 1e-5, worst_f   # north_star: 1e-5 relative on fused float32 voxels
+    else:
+        assert worst_f <= 1.0 and frac_f <= 1e-3, (worst_f, frac_f)
 
 
 def test_rl_midsize_against_oracle(cuda):
