@@ -496,8 +496,9 @@ def run_b200(args):
         return mv.fuse_blockwise_arrays(tv, params, sp_slab, props)
 
     fused_host = e2e_step()
+    fusion.TRANSFER["h2d_bytes"] = 0
     fused_host = e2e_step()
-    h2d = sum(h.nbytes for h in host_views)
+    h2d = int(fusion.TRANSFER["h2d_bytes"])   # what the entry points actually sent: whole views at N = 1, the slab's source bricks beyond
     d2h = fused_host.nbytes
     barrier()
     e_steps = max(3, min(args.steps, 6))
@@ -509,6 +510,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = nvox / (float(t.item()) / e_steps) / 1e9
+    if world > 1:   # whole-job bytes per step: every rank's uploads and its slab of the result
+        tb = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+        dist.all_reduce(tb)
+        h2d, d2h = int(tb[0].item()), int(tb[1].item())
 
     # ---- for comparison: the pipelined device API (pinned views -> H2D -> fused kernel -> D2H) ------------
     pinned = [torch.from_numpy(np.asarray(h)) for h in host_views]
@@ -575,7 +580,8 @@ def run_b200(args):
                 "clocks": clk.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e_val, "unit": "Gvoxel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "mvregfus_b200.multiview.transform_stack_dask_numpy x%d + fuse_blockwise_arrays, host numpy "
-                               "buffers in page-locked memory" % NVIEWS},
+                               "buffers in page-locked memory (whole views; a z-slab rank uploads the source bricks of its "
+                               "slab, the reference's per-chunk crop mv:1552-1601)" % NVIEWS},
                 "e2e_device_api": {"value": dev_api_val, "unit": "Gvoxel/s",
                                    "api": "fusion.fuse_blend on device tensors, copies of consecutive steps pipelined on 3 streams"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",

@@ -255,6 +255,12 @@ int mvf_background_u16(const uint16_t* in, uint16_t* out, size_t n, uint32_t lev
 int mvf_bin_shrink(const void* in, int dtype, const int32_t in_dims[3], const int32_t factors[3], void* out,
                    void* stream);
 
+/* ---- source brick of a target box: strided host -> device copy ---------------------------------------------
+ * view[lo:hi] (zyx, C-contiguous host array of `dims`) -> dense device brick, one cudaMemcpy3DAsync: what a z-slab rank
+ * uploads instead of whole views (the per-chunk crop of transform_chunk, mv:1552-1601). */
+int mvf_copy_brick_h2d(const void* host, int dtype, const int32_t dims[3], const int32_t lo[3], const int32_t hi[3],
+                       void* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -263,3 +263,26 @@ extern "C" int mvf_bin_shrink(const void* in, int dtype, const int32_t in_dims[3
   MVF_LAUNCHED();
   return MVF_OK;
 }
+
+// ---- strided host -> device copy of a source brick ---------------------------------------------------------------
+// The reference crops every view to the bounding box a chunk touches before resampling (mv:1552-1601); a z-slab rank
+// does the same with its slab.  One cudaMemcpy3DAsync moves view[lo:hi] out of the caller's array (page-locked: a
+// single DMA with a row pitch; pageable: staged by the driver) into a dense device brick.
+extern "C" int mvf_copy_brick_h2d(const void* host, int dtype, const int32_t dims[3], const int32_t lo[3],
+                                  const int32_t hi[3], void* dst, void* stream) {
+  MVF_CHECK_ARG(host && dims && lo && hi && dst, "NULL argument");
+  MVF_CHECK_ARG(dtype == MVF_U16 || dtype == MVF_F32, "dtype must be MVF_U16 or MVF_F32");
+  for (int d = 0; d < 3; ++d) MVF_CHECK_ARG(lo[d] >= 0 && hi[d] > lo[d] && hi[d] <= dims[d], "brick must lie inside the view");
+  const size_t esz = dtype == MVF_U16 ? 2 : 4;
+  const size_t w = (size_t)(hi[2] - lo[2]), h = (size_t)(hi[1] - lo[1]), dep = (size_t)(hi[0] - lo[0]);
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(host), (size_t)dims[2] * esz, (size_t)dims[2] * esz, (size_t)dims[1]);
+  p.srcPos = make_cudaPos((size_t)lo[2] * esz, (size_t)lo[1], (size_t)lo[0]);
+  p.dstPtr = make_cudaPitchedPtr(dst, w * esz, w * esz, h);
+  p.dstPos = make_cudaPos(0, 0, 0);
+  p.extent = make_cudaExtent(w * esz, h, dep);
+  p.kind = cudaMemcpyHostToDevice;
+  MVF_CUDA(cudaMemcpy3DAsync(&p, as_stream(stream)));
+  return MVF_OK;
+}

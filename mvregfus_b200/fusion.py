@@ -29,6 +29,9 @@ def dtype_code(t):
     raise TypeError("views must be uint16 or float32, got %s" % (t.dtype,))
 
 
+TRANSFER = {"h2d_bytes": 0}   # bytes this process has sent to the device through to_device / upload_brick (bench accounting)
+
+
 def to_device(arr, device=None):
     """numpy (uint16/float32, any layout) -> contiguous CUDA tensor.  Page-locked host memory (``pinned_empty``) is
     copied asynchronously on the current stream; pageable memory goes through the driver's staging copy."""
@@ -40,6 +43,7 @@ def to_device(arr, device=None):
         else:
             raise TypeError("unsupported voxel dtype %s (uint16 and float32 are supported)" % arr.dtype)
     t = torch.from_numpy(arr)
+    TRANSFER["h2d_bytes"] += arr.nbytes
     return t.to(device or "cuda", non_blocking=t.is_pinned())
 
 
@@ -163,10 +167,12 @@ class ViewSet:
 
 
 def build_viewset(tensors, orig_stack_propertiess, params, stack_properties, weights="blending",
-                  coarse=None, view_dims=None, probe=True):
+                  coarse=None, view_dims=None, probe=True, windows=None):
     """Fill ``mvf_view`` for every view.  ``tensors`` may be None (weights only).  ``coarse`` is an optional
     ``(grids (V,cz,cy,cx) float32, origin[3], spacing[3])`` for the DCT mode.  ``weights`` in
-    {'blending', 'dct', None}."""
+    {'blending', 'dct', None}.  ``windows``: optional first index (z, y, x) of every tensor inside its view when only the
+    source brick of the target box was uploaded (the reference's own per-chunk crop, mv:1552-1601): the data map is
+    shifted by it, weights keep the geometry of the whole view."""
     n = len(params)
     if n > _cabi.MVF_MAX_VIEWS:
         raise ValueError("at most %d views per fused pass (got %d)" % (_cabi.MVF_MAX_VIEWS, n))
@@ -181,7 +187,7 @@ def build_viewset(tensors, orig_stack_propertiess, params, stack_properties, wei
         v_or = np.asarray(osp["origin"], dtype=np.float64)
         M, off = index_space_affine(params[i], v_sp, v_or, out_sp, out_or)
         s.matrix = _cabi.f64(M.ravel(), 9)
-        s.offset = _cabi.f64(off, 3)
+        s.offset = _cabi.f64(off if windows is None else off - np.asarray(windows[i], dtype=np.float64), 3)
         if tensors is not None:
             t = tensors[i]
             if not t.is_contiguous() or t.dim() != 3:
@@ -275,4 +281,21 @@ def fuse_weighted(views, weights, out=None, out_f32=None):
                                C.c_void_p(out_f32.data_ptr()) if out_f32 is not None else None,
                                views[0].numel(), _stream_ptr())
     _cabi.check(rc)
+    return out
+
+
+def upload_brick(host_array, lo, hi, device="cuda"):
+    """host_array[lo0:hi0, lo1:hi1, lo2:hi2] as a contiguous CUDA tensor, moved by ONE strided DMA (cudaMemcpy3DAsync
+    inside mvf_copy_brick_h2d) straight out of the caller's (ideally page-locked) array - no host-side gather."""
+    a = np.asarray(host_array)
+    if a.ndim != 3 or not a.flags.c_contiguous or a.dtype not in (np.dtype(np.uint16), np.dtype(np.float32)):
+        a = np.ascontiguousarray(a)
+        if a.dtype not in (np.dtype(np.uint16), np.dtype(np.float32)):
+            a = a.astype(np.float32)
+    lo, hi = [int(x) for x in lo], [int(x) for x in hi]
+    out = torch.empty([h - l for l, h in zip(lo, hi)], dtype=torch.uint16 if a.dtype == np.uint16 else torch.float32, device=device)
+    _cabi.check(_cabi.load().mvf_copy_brick_h2d(C.c_void_p(a.ctypes.data), dtype_code(out), _cabi.i32x3(a.shape), _cabi.i32x3(lo),
+                                                _cabi.i32x3(hi), C.c_void_p(out.data_ptr()), _stream_ptr()))
+    out._mvf_host_keepalive = a   # the copy is asynchronous
+    TRANSFER["h2d_bytes"] += out.numel() * out.element_size()
     return out

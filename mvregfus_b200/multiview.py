@@ -489,8 +489,23 @@ def _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_properties
             return None
     if len(tviews) > 8 or len({t.dtype for t in tviews}) != 1:
         return None
-    dviews = [fusion.to_device(t.stack) for t in tviews]
-    fused = pipeline.fuse_volume_blockwise(dviews, orig_stack_propertiess, params, stack_properties)
+    # Upload per view only the source brick the target box touches (the reference's per-chunk crop, mv:1552-1601): for a
+    # z-slab of the fused frame that is a fraction of every view; whole views go up in one piece.
+    from . import slab
+    dviews, windows = [], []
+    for t in tviews:
+        vshape = np.asarray(np.asarray(t.stack).shape)
+        matrix, offset = index_space_affine(t.p, t.stack.spacing, t.stack.origin, t.spacing, t.origin)
+        lo, hi = slab.source_brick(matrix, offset, vshape, 0, size[0], size[1], size[2])
+        lo = np.minimum(lo, vshape - 1)
+        hi = np.maximum(hi, lo + 1)
+        if os.environ.get("MVF_BRICK_UPLOAD", "1") == "0" or np.prod(hi - lo) >= 0.8 * np.prod(vshape):
+            dviews.append(fusion.to_device(t.stack))
+            windows.append(np.zeros(3, dtype=np.int64))
+        else:
+            dviews.append(fusion.upload_brick(t.stack, lo, hi))
+            windows.append(lo)
+    fused = pipeline.fuse_volume_blockwise(dviews, orig_stack_propertiess, params, stack_properties, windows=windows)
     if tviews[0].dtype != np.uint16:   # the block loop assembles its result in the dtype of the views
         fused = fused.to(torch.int32).to(torch.float32)
     return fusion.to_host(fused)

@@ -40,14 +40,16 @@ def chunk_decisions(data_bits, weight_bits, probe_ok):
     return info
 
 
-def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_properties, chunk=CHUNK, out=None):
+def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_properties, chunk=CHUNK, out=None, windows=None):
     """views: list of CUDA tensors (raw views).  Returns the fused uint16 CUDA tensor of stack_properties['size'],
     equal to what fuse_blockwise(..., weights_func=get_weights_simple, fusion_func=fuse_views_weights) produces."""
     lib = _cabi.load()
     dims = [int(s) for s in stack_properties["size"]]
     nch = [-(-d // chunk) for d in dims]
     dev = views[0].device
-    vs = fusion.build_viewset(views, orig_stack_propertiess, params, stack_properties, weights="blending", probe=False)
+    # (windows: first view index of every tensor when only the source bricks of this box were uploaded)
+    vs = fusion.build_viewset(views, orig_stack_propertiess, params, stack_properties, weights="blending", probe=False,
+                              windows=windows)
     flags = torch.zeros((2, int(np.prod(nch))), dtype=torch.int32, device=dev)
     st = fusion._stream_ptr()
     for probe in (0, 1):

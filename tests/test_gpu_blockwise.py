@@ -119,3 +119,38 @@ def test_device_resident_block_loop_equals_host_block_loop(cuda, mode, monkeypat
                                fusion_kwargs=dict(kw))
         d = np.abs(got.astype(np.int64) - np.asarray(ref).astype(np.int64))
         assert d.max() <= 3 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+def test_slab_box_uploads_source_bricks_only(cuda, dtype, monkeypatch):
+    """A z-slab of the fused frame through the drop-in socket (lazy transformed views -> fuse_blockwise_arrays): only the
+    source brick of the slab is uploaded per view (z range of the 0/180 degree views, x range of the 90/270 degree ones -
+    the reference's per-chunk crop, mv:1552-1601).  Same result, bit for bit, as with whole views on the device, and equal
+    to the oracle's block loop on the slab frame."""
+    from mvregfus_b200 import multiview as mv, synthetic
+    from mvregfus_b200.image_array import ImageArray
+    shape = (96, 80, 112)
+    views, params, props = synthetic.make_views(shape, 4, dtype=dtype, seed=21)
+    views = [ImageArray(v, spacing=p["spacing"], origin=p["origin"]) for v, p in zip(views, props)]
+    sp = mv.calc_stack_properties_from_views_and_params(props, params, spacing=[1.0] * 3)
+    size = [int(s) for s in sp["size"]]
+    z0, z1 = 40, 72
+    sp_slab = {"size": np.array([z1 - z0, size[1], size[2]]), "spacing": sp["spacing"],
+               "origin": sp["origin"] + np.array([z0, 0, 0]) * sp["spacing"]}
+    calls = []
+    from mvregfus_b200 import fusion
+    real = fusion.upload_brick
+    monkeypatch.setattr(fusion, "upload_brick", lambda a, lo, hi, **k: (calls.append((tuple(lo), tuple(hi))), real(a, lo, hi, **k))[1])
+
+    def run():
+        tv = [mv.transform_stack_dask_numpy(v, p, stack_properties=sp_slab) for v, p in zip(views, params)]
+        return np.asarray(mv.fuse_blockwise_arrays(tv, params, sp_slab, props))
+    got = run()
+    assert len(calls) == 4 and all(np.prod(np.array(hi) - np.array(lo)) < 0.8 * np.prod(shape) for lo, hi in calls)
+    monkeypatch.setenv("MVF_BRICK_UPLOAD", "0")
+    whole = run()
+    assert len(calls) == 4 and got.dtype == whole.dtype == dtype and np.array_equal(got, whole)
+    tvo = [O.transform_stack_dask_numpy(v, p, sp_slab) for v, p in zip(views, params)]
+    ref = np.asarray(O.fuse_blockwise(tvo, params, sp_slab, props, fusion_block_overlap=0))
+    d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 3 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
