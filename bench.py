@@ -330,9 +330,12 @@ def run_rl(dev, rank=0, world=1):
     else:  # z-slab of this rank; PSF-radius halos travel over NVLink inside plan.iterate()
         import torch.distributed as dist
         from mvregfus_b200 import slab
-        z0, z1 = slab.slab_bounds(shape[0], world)[rank]
+        # slabs balanced by work: rank 0 also blurs the planes its wrap-around refers to and the boundary ratios
+        kz = int(np.asarray(psfs[0]).shape[0])
+        bounds = slab.rl_slab_bounds(shape[0], world, kz, (int(_cabi.load().mvf_rl_padded_size(kz)) - 1) // 2)
+        z0, z1 = bounds[rank]
         plan = rl.SlabRLPlan([t[z0:z1].clone() for t in tviews], [w[v][z0:z1].clone() for v in range(NVIEWS)], psfs,
-                             shape[0], rank, world)
+                             shape[0], rank, world, bounds=bounds)
     halo_txt = ("pulled from the neighbours' symmetric-memory buffers, iteration replayed from a CUDA graph"
                 if getattr(plan, "symm", None) is not None else "NCCL ring isend/irecv")
     plan.init_estimate()
@@ -359,7 +362,6 @@ def run_rl(dev, rank=0, world=1):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         # parity of the sharded run: gather the slabs on rank 0, compare with the whole volume computed there
-        bounds = slab.slab_bounds(shape[0], world)
         est = plan.est.contiguous()
         if rank == 0:
             whole = torch.empty(shape, dtype=torch.float32, device=dev)
@@ -391,7 +393,7 @@ def run_rl(dev, rank=0, world=1):
                                    "sigma z=%g xy=%g (19^3, separable), %d iterations" % (NVIEWS, *shape, *RL_SIGMA, RL_ITERS)},
             "kernel_launches_per_iteration": launches_per_iteration,
             "cuda_graph": graphed,
-            "n_gpus": world, "scaling": "strong",
+            "n_gpus": world, "scaling": "strong", "slab_planes": [b - a for a, b in bounds] if world > 1 else [shape[0]],
             "sharding": "whole volume" if world == 1 else "z-slabs, PSF-radius halos over NVLink (%s)" % halo_txt,
             "parity_vs_whole": parity,
             "roofline": {"bound": "hbm", "achieved": alg / (per_it * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",

@@ -22,6 +22,31 @@ def slab_bounds(nz, world):
     return bounds
 
 
+def rl_slab_bounds(nz, world, ksize_z, rp):
+    """z ranges for the v4 RL schedule, balanced by WORK rather than planes.  Every rank blurs its halo planes once per
+    x/y group besides its own planes; rank 0 holds 5*rp halo planes (3*rp below the top of the volume for the wrap-around,
+    2*rp above its slab) against 4*rp in the middle and 2*rp on the last rank, and ranks 0 and last compute the boundary
+    ratios.  Measured on 8 B200 (tools/rl_slab_phases.py): a halo plane costs about a third of an own plane, the boundary
+    ratios about 6.5 own planes - with equal slabs rank 0 keeps everybody waiting at the barrier for 0.3 ms of 3.6."""
+    nz, world = int(nz), int(world)
+    if world == 1:
+        return [(0, nz)]
+    halo = np.array([5 * rp] + [4 * rp] * (world - 2) + [2 * rp], dtype=np.float64)
+    side = np.array([6.5] + [0.0] * (world - 2) + [6.5])
+    fixed = 0.33 * halo + side
+    own = (nz + fixed.sum()) / world - fixed            # equal total cost
+    n = np.floor(own).astype(int)
+    order = np.argsort(-(own - n))
+    for i in order[:nz - int(n.sum())]:
+        n[i] += 1
+    need = np.full(world, 2 * rp)
+    need[-1] = max(need[-1], ksize_z + 2 + rp)
+    if np.any(n < need) or n.sum() != nz:                # thin slabs: the plain partition (the planners reject what cannot work)
+        return slab_bounds(nz, world)
+    z = np.concatenate([[0], np.cumsum(n)])
+    return [(int(a), int(b)) for a, b in zip(z[:-1], z[1:])]
+
+
 def source_brick(matrix, offset, view_shape, z0, z1, ny, nx):
     """Index box of a view that the slab [z0,z1) touches: the reference's own chunk bounding box (corners
     through matrix', +-2, clipped; mv:1552-1571) applied to the slab.  Returns (lo[3], hi[3]) int64."""
@@ -42,9 +67,9 @@ class HaloPlan:
     """Plane bookkeeping of one rank's halo-padded slab buffer: planes [0,rp) = lower halo, [rp, rp+nzl) = own
     planes, [rp+nzl, nzl+2rp) = upper halo."""
 
-    def __init__(self, nz, world, rank, ksize_z, rp):
+    def __init__(self, nz, world, rank, ksize_z, rp, bounds=None):
         self.nz, self.world, self.rank, self.K, self.rp = int(nz), int(world), int(rank), int(ksize_z), int(rp)
-        self.bounds = slab_bounds(nz, world)
+        self.bounds = slab_bounds(nz, world) if bounds is None else [(int(a), int(b)) for a, b in bounds]
         self.z0, self.z1 = self.bounds[rank]
         self.nzl = self.z1 - self.z0
         if world > 1 and min(b - a for a, b in self.bounds) < max(2 * rp + 1, ksize_z + 3 + rp):
@@ -163,7 +188,7 @@ class SymmetricHalo:
         self.bufs = [self.store[i][:plan.nzl + 2 * plan.rp] for i in range(nbuf)]
         rp = plan.rp
         # source planes inside the neighbours' padded buffers (their own planes start at rp)
-        lower = HaloPlan(plan.nz, plan.world, plan.lower_src, plan.K, rp)
+        lower = HaloPlan(plan.nz, plan.world, plan.lower_src, plan.K, rp, plan.bounds)
         self.lower_peer = self.hdl.get_buffer(plan.lower_src, self.shape, torch.float32)
         idx = lower.planes_for_upper_neighbour() + rp
         self.lower_slice = slice(int(idx[0]), int(idx[-1]) + 1) if np.all(np.diff(idx) == 1) else None
@@ -202,9 +227,12 @@ class ZZLayout:
     nz-2-K-rp instead (sources of the wrap-around).  Padded (masked) views: [rp][own][rp]; on rank 0 the front block
     holds planes [nz-2-K, nz-2-K+rp)."""
 
-    def __init__(self, nz, world, rank, ksize_z, rp):
+    def __init__(self, nz, world, rank, ksize_z, rp, bounds=None):
         self.nz, self.world, self.rank, self.K, self.rp = int(nz), int(world), int(rank), int(ksize_z), int(rp)
-        self.bounds = slab_bounds(nz, world)
+        self.bounds = slab_bounds(nz, world) if bounds is None else [(int(a), int(b)) for a, b in bounds]
+        if len(self.bounds) != self.world or self.bounds[0][0] != 0 or self.bounds[-1][1] != self.nz or \
+                any(a[1] != b[0] for a, b in zip(self.bounds[:-1], self.bounds[1:])):
+            raise ValueError("slab bounds must tile [0, nz) in rank order")
         self.z0, self.z1 = self.bounds[rank]
         self.nzl = self.z1 - self.z0
         self.front, self.back = 3 * self.rp, 2 * self.rp
@@ -298,7 +326,7 @@ class ZZLayout:
 
     # ---- plane transfers: (src_rank, first src local plane, count, first dst local plane) --------------------------------
     def _peer(self, r):
-        return ZZLayout(self.nz, self.world, r, self.K, self.rp)
+        return ZZLayout(self.nz, self.world, r, self.K, self.rp, self.bounds)
 
     def est_transfers(self):
         """Halo fills of the padded estimate, every iteration (sources are OWN planes of the peers)."""

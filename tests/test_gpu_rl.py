@@ -299,3 +299,26 @@ def test_rl_long_separable_psfs_match_oracle(cuda, ksize, kernel, monkeypatch):
         assert torch.equal(got, whole)        # same kernels, same accumulation order
     else:                                     # v3 slabs against a v4 whole volume: other summation order
         assert float(((got - whole).abs() / whole.abs().clamp_min(1.0)).max()) <= 1e-4
+
+
+@pytest.mark.parametrize("kernel", ["v3", "v4"])
+def test_rl_unequal_slabs_equal_whole(cuda, kernel, monkeypatch):
+    """Slabs of different heights (slab.rl_slab_bounds balances the v4 schedule by work; any tiling is accepted)."""
+    import torch
+    from mvregfus_b200 import fusion, rl, slab, multiview as mv
+    monkeypatch.setenv("MVF_RL_KERNEL", kernel)
+    tv, w, params, sp = _axis_case(shape=(90, 40, 48), nviews=2)
+    psfs = [mv.get_psf(p, sp, 2, 1) for p in params]   # 7^3
+    dv, dw = [fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w]
+    whole = rl.RLPlan(dv, dw, psfs).run(num_iterations=3)
+    nz = dv[0].shape[0]
+    for bounds in (slab.rl_slab_bounds(nz, 3, 7, 3), [(0, 22), (22, 57), (57, nz)]):
+        plans = [rl.SlabRLPlan([v[a:b].contiguous() for v in dv], [x[a:b].contiguous() for x in dw], psfs, nz, r, 3, bounds=bounds)
+                 for r, (a, b) in enumerate(bounds)]
+        assert all(p.zz == (kernel == "v4") for p in plans)
+        rl.setup_emulated(plans)
+        for p in plans:
+            p.init_estimate()
+        for _ in range(3):
+            rl.iterate_emulated(plans)
+        assert torch.equal(torch.cat([p.est for p in plans], 0), whole)

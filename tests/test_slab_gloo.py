@@ -140,3 +140,28 @@ def test_zz_transfers_gloo(world, nz, K, rp):
     out = mgr.dict()
     mp.spawn(_zz_worker, args=(world, port, nz, K, rp, out), nprocs=world, join=True)
     assert all(out[r] is True for r in range(world)), dict(out)
+
+
+def test_rl_slab_bounds_balance_and_layout():
+    """Work-balanced slabs of the v4 schedule: they tile the volume, rank 0 (extra wrap-around planes + boundary ratios)
+    gets fewer planes, thin volumes fall back to equal slabs, and the plane bookkeeping holds for unequal slabs."""
+    b = slab.rl_slab_bounds(512, 8, 19, 9)
+    sizes = [z1 - z0 for z0, z1 in b]
+    assert b[0][0] == 0 and b[-1][1] == 512 and all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+    assert sizes[0] < min(sizes[1:]) and max(sizes[1:]) - min(sizes[1:]) <= 1
+    assert slab.rl_slab_bounds(64, 4, 19, 9) == slab.slab_bounds(64, 4)
+    assert slab.rl_slab_bounds(40, 1, 7, 3) == [(0, 40)]
+    nz, world, K, rp = 200, 3, 9, 6
+    bounds = slab.rl_slab_bounds(nz, world, K, rp)
+    lays = [slab.ZZLayout(nz, world, r, K, rp, bounds) for r in range(world)]
+    assert [l.nzl for l in lays] == [z1 - z0 for z0, z1 in bounds]
+    est = [np.full(l.height, -1) for l in lays]
+    view = [np.full(l.vheight, -1) for l in lays]
+    for l, e, v in zip(lays, est, view):
+        e[l.front:l.front + l.nzl] = np.arange(l.z0, l.z1)
+        v[l.rp:l.rp + l.nzl] = np.arange(l.z0, l.z1)
+    slab.run_transfers_local(est, lays, "est_transfers")
+    slab.run_transfers_local(view, lays, "view_transfers")
+    assert all(_zz_check(l, e, v, nz, K, rp) for l, e, v in zip(lays, est, view))
+    with pytest.raises(ValueError):
+        slab.ZZLayout(nz, world, 0, K, rp, [(0, 60), (70, 140), (140, 200)])

@@ -11,8 +11,9 @@ dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
 torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
 tviews, w, psfs = bench.rl_inputs(dev)
-z0, z1 = slab.slab_bounds(bench.RL_SHAPE[0], world)[rank]
-plan = rl.SlabRLPlan([t[z0:z1].clone() for t in tviews], [w[v][z0:z1].clone() for v in range(len(tviews))], psfs, bench.RL_SHAPE[0], rank, world)
+bounds = slab.rl_slab_bounds(bench.RL_SHAPE[0], world, 19, 9) if os.environ.get("RL_BALANCED", "1") == "1" else slab.slab_bounds(bench.RL_SHAPE[0], world)
+z0, z1 = bounds[rank]
+plan = rl.SlabRLPlan([t[z0:z1].clone() for t in tviews], [w[v][z0:z1].clone() for v in range(len(tviews))], psfs, bench.RL_SHAPE[0], rank, world, bounds=bounds)
 del tviews, w
 plan.init_estimate()
 for _ in range(3):
