@@ -607,15 +607,17 @@ class SlabRLPlan:
             for g, ps in groups:
                 run(g, ps, lo, lay.front + lay.nzl + nback - lo)
             return
-        # only the first group is split (its own planes cover the halo copies); the others run as ONE launch over the whole
+        # only the first two groups are split (their own planes cover the halo copies); the others run as ONE launch over the whole
         # contiguous plane range afterwards - launches of 18 halo planes fill half the GPU (measured at N = 8: 3.9 us per
         # plane and view against 2.9 us in the 64-plane launches)
-        g0, ps0 = groups[0]
-        run(g0, ps0, lay.front, lay.nzl)
+        split = groups[:2]   # (two groups of own planes outlast the pull of 5 * rp planes on rank 0)
+        for g, ps in split:
+            run(g, ps, lay.front, lay.nzl)
         join()
-        run(g0, ps0, lo, lay.front - lo)
-        run(g0, ps0, lay.front + lay.nzl, nback)
-        for g, ps in groups[1:]:
+        for g, ps in split:
+            run(g, ps, lo, lay.front - lo)
+            run(g, ps, lay.front + lay.nzl, nback)
+        for g, ps in groups[2:]:
             run(g, ps, lo, lay.front + lay.nzl + nback - lo)
 
     def _zz_view(self, v, before_update=None):

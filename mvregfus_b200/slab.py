@@ -26,14 +26,15 @@ def rl_slab_bounds(nz, world, ksize_z, rp):
     """z ranges for the v4 RL schedule, balanced by WORK rather than planes.  Every rank blurs its halo planes once per
     x/y group besides its own planes; rank 0 holds 5*rp halo planes (3*rp below the top of the volume for the wrap-around,
     2*rp above its slab) against 4*rp in the middle and 2*rp on the last rank, and ranks 0 and last compute the boundary
-    ratios.  Measured on 8 B200 (tools/rl_slab_phases.py): a halo plane costs about a third of an own plane, the boundary
-    ratios about 6.5 own planes - with equal slabs rank 0 keeps everybody waiting at the barrier for 0.3 ms of 3.6."""
+    ratios.  Measured on 8 B200 (tools/rl_slab_phases.py, configs[3]): a halo plane costs 0.3 own planes (x/y passes
+    only), the boundary ratios 10.5 own planes (0.1 ms per view) - with equal slabs rank 0 keeps everybody waiting at the
+    barrier for 0.3 ms of 3.6."""
     nz, world = int(nz), int(world)
     if world == 1:
         return [(0, nz)]
     halo = np.array([5 * rp] + [4 * rp] * (world - 2) + [2 * rp], dtype=np.float64)
-    side = np.array([6.5] + [0.0] * (world - 2) + [6.5])
-    fixed = 0.33 * halo + side
+    side = np.array([10.5] + [0.0] * (world - 2) + [10.5])
+    fixed = 0.3 * halo + side
     own = (nz + fixed.sum()) / world - fixed            # equal total cost
     n = np.floor(own).astype(int)
     order = np.argsort(-(own - n))

@@ -144,11 +144,11 @@ def test_zz_transfers_gloo(world, nz, K, rp):
 
 def test_rl_slab_bounds_balance_and_layout():
     """Work-balanced slabs of the v4 schedule: they tile the volume, rank 0 (extra wrap-around planes + boundary ratios)
-    gets fewer planes, thin volumes fall back to equal slabs, and the plane bookkeeping holds for unequal slabs."""
+    and the last rank (boundary ratios) get fewer planes, thin volumes fall back to equal slabs, and the plane bookkeeping holds for unequal slabs."""
     b = slab.rl_slab_bounds(512, 8, 19, 9)
     sizes = [z1 - z0 for z0, z1 in b]
     assert b[0][0] == 0 and b[-1][1] == 512 and all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
-    assert sizes[0] < min(sizes[1:]) and max(sizes[1:]) - min(sizes[1:]) <= 1
+    assert sizes[0] < sizes[-1] < min(sizes[1:-1]) and max(sizes[1:-1]) - min(sizes[1:-1]) <= 1
     assert slab.rl_slab_bounds(64, 4, 19, 9) == slab.slab_bounds(64, 4)
     assert slab.rl_slab_bounds(40, 1, 7, 3) == [(0, 40)]
     nz, world, K, rp = 200, 3, 9, 6
