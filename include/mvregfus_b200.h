@@ -226,6 +226,17 @@ int mvf_rl_fft_blur(void* plan, const float* in, const int32_t* zmap, int zmap_r
                     const void* psf_spectrum, float* real_buf, void* cplx_buf, int mode,
                     const void* view, int dtype, const float* weights, float* out, int first, int last,
                     float* est, int64_t est_offset, double* sum_out, void* stream);
+/* PSFs of views rotated about y factor as a(y) (x) B(z, x): a zx plan runs the circular convolution as batched 2-D (z, x)
+ * transforms with y as the batch (a third less FFT work, no padding along y) and the y pass as a direct K-tap
+ * convolution inside the epilogue kernel (ksize[1] <= 43).  mvf_rl_fft_psf_spectrum then takes the (kz, 1, kx) factor B,
+ * mvf_rl_fft_blur_zx the taps a(y) as a host array; buffers are sized from mvf_rl_fft_plan_padded. */
+int mvf_rl_fft_plan_create_zx(const int32_t dims[3], const int32_t ksize[3], void* workspace_or_null,
+                              size_t* workspace_bytes, void** plan_out);
+int mvf_rl_fft_plan_padded(void* plan, int32_t padded[3]);
+int mvf_rl_fft_blur_zx(void* plan, const float* in, const int32_t* zmap, int zmap_radius, const int32_t ksize[3],
+                       const float* host_ky, const void* psf_spectrum, float* real_buf, void* cplx_buf, int mode,
+                       const void* view, int dtype, const float* weights, float* out, int first, int last,
+                       float* est, int64_t est_offset, double* sum_out, void* stream);
 
 /* ---- K3: DCT-entropy quality of blocks of a transformed view (determine_chunk_quality, mv:4496-4561) --
  * For every job (linear index into the nblocks grid) the size^3 block is read with stride `bin` from the

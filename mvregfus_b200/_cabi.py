@@ -23,7 +23,7 @@ EXPORTS = (
     "mvf_rl_padded_size", "mvf_rl_init_estimate", "mvf_rl_blur", "mvf_rl_ratio", "mvf_rl_correct",
     "mvf_dct_scratch_bytes", "mvf_dct_entropy",
     "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
-    "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur",
+    "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur", "mvf_rl_fft_plan_create_zx", "mvf_rl_fft_plan_padded", "mvf_rl_fft_blur_zx",
     "mvf_rl_stream_supported", "mvf_rl_xy", "mvf_rl_blur_z", "mvf_rl_ratio_z", "mvf_rl_correct_z",
     "mvf_rl_zz", "mvf_rl_xy_correct", "mvf_copy_brick_h2d",
     "mvf_subsample", "mvf_range_u16", "mvf_hist_u16", "mvf_background_u16", "mvf_bin_shrink",
@@ -105,6 +105,11 @@ def _declare(lib):
     lib.mvf_rl_fft_blur.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, i32p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_void_p]
+    lib.mvf_rl_fft_plan_create_zx.argtypes = lib.mvf_rl_fft_plan_create.argtypes
+    lib.mvf_rl_fft_plan_padded.argtypes = [C.c_void_p, i32p]
+    lib.mvf_rl_fft_blur_zx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, i32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_int64, C.c_void_p, C.c_void_p]
     lib.mvf_dct_scratch_bytes.argtypes = [C.c_int, C.POINTER(C.c_int)]
     lib.mvf_dct_entropy.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int, C.c_int, i32p, C.c_void_p, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]

@@ -29,6 +29,22 @@ def factor_psf(psf, tol=2e-6):
     return (kz / total).astype(np.float32), (ky / total).astype(np.float32), kx.astype(np.float32)
 
 
+def factor_psf_y(psf, tol=2e-6):
+    """(a, B) with psf ~= a(y) (x) B(z, x), or None.  A view rotated about the y axis has such a PSF: get_psf resamples a
+    separable Gaussian with a map that leaves y alone (mv:5376-5418), so only the (z, x) part loses separability - and that
+    part is far from low rank.  The convolution then needs FFTs over (z, x) only."""
+    if os.environ.get("MVF_RL_FFT", "zx") == "3d":
+        return None
+    p = np.asarray(psf, dtype=np.float64)
+    total = p.sum()
+    if not np.isfinite(total) or total == 0 or p.shape[1] > _cabi.MVF_RL_KMAX or p.shape[1] % 2 == 0:
+        return None
+    a, B = p.sum((0, 2)), p.sum(1)
+    if np.max(np.abs(a[None, :, None] * B[:, None, :] / total - p)) > tol * np.max(np.abs(p)):
+        return None
+    return (a / total).astype(np.float32), np.ascontiguousarray(B, dtype=np.float32)
+
+
 def too_long_for_kernels(psf):
     """PSFs longer than MVF_RL_KMAX taps per axis (sz / spacing large) only fit the cuFFT convolution."""
     return int(max(np.asarray(psf).shape)) > _cabi.MVF_RL_KMAX
@@ -61,16 +77,17 @@ class FftBlur:
     """cuFFT convolution state shared by the non-separable views of one RL problem: plan, work area, one real and
     one half-spectrum buffer, and one PSF spectrum per view."""
 
-    def __init__(self, dims, ksize, device):
+    def __init__(self, dims, ksize, device, zx=False):
+        """zx: batched 2-D (z, x) transforms + direct y pass, for PSFs a(y) (x) B(z, x) (factor_psf_y)."""
         self.lib = _cabi.load()
-        self.dims, self.ksize = tuple(int(d) for d in dims), tuple(int(k) for k in ksize)
-        padded = (C.c_int32 * 3)()
-        _cabi.check(self.lib.mvf_rl_fft_padded_dims(_cabi.i32x3(self.dims), _cabi.i32x3(self.ksize), padded))
-        self.padded = tuple(int(x) for x in padded)
+        self.dims, self.ksize, self.zx = tuple(int(d) for d in dims), tuple(int(k) for k in ksize), bool(zx)
         nbytes = C.c_size_t(0)
         self.plan = C.c_void_p()
-        _cabi.check(self.lib.mvf_rl_fft_plan_create(_cabi.i32x3(self.dims), _cabi.i32x3(self.ksize), None,
-                                                    C.byref(nbytes), C.byref(self.plan)))
+        create = self.lib.mvf_rl_fft_plan_create_zx if zx else self.lib.mvf_rl_fft_plan_create
+        _cabi.check(create(_cabi.i32x3(self.dims), _cabi.i32x3(self.ksize), None, C.byref(nbytes), C.byref(self.plan)))
+        padded = (C.c_int32 * 3)()
+        _cabi.check(self.lib.mvf_rl_fft_plan_padded(self.plan, padded))
+        self.padded = tuple(int(x) for x in padded)
         self.work = torch.empty(max(int(nbytes.value), 16), dtype=torch.uint8, device=device)
         _cabi.check(self.lib.mvf_rl_fft_plan_set_workspace(self.plan, C.c_void_p(self.work.data_ptr())))
         L = self.padded
@@ -79,14 +96,35 @@ class FftBlur:
         self.device = device
 
     def spectrum(self, psf):
-        psf_d = torch.from_numpy(np.ascontiguousarray(psf, dtype=np.float32)).to(self.device)
+        """3-D plan: spectrum of the padded PSF.  zx plan: `psf` is the pair (a, B) of factor_psf_y; returns (spectrum of
+        B, taps a) - what blur() takes as `spec`."""
         L = self.padded
+        if self.zx:
+            a, B = psf
+            psf_d = torch.from_numpy(np.ascontiguousarray(B, dtype=np.float32)).to(self.device)
+            spec = torch.empty((L[0], L[2] // 2 + 1, 2), dtype=torch.float32, device=self.device)
+            _cabi.check(self.lib.mvf_rl_fft_psf_spectrum(self.plan, C.c_void_p(psf_d.data_ptr()), _cabi.i32x3((B.shape[0], 1, B.shape[1])),
+                                                         C.c_void_p(self.real.data_ptr()), C.c_void_p(spec.data_ptr()), _stream_ptr()))
+            return spec, np.ascontiguousarray(a, dtype=np.float32)
+        psf_d = torch.from_numpy(np.ascontiguousarray(psf, dtype=np.float32)).to(self.device)
         spec = torch.empty((L[0], L[1], L[2] // 2 + 1, 2), dtype=torch.float32, device=self.device)
         _cabi.check(self.lib.mvf_rl_fft_psf_spectrum(self.plan, C.c_void_p(psf_d.data_ptr()), _cabi.i32x3(psf.shape),
                                                      C.c_void_p(self.real.data_ptr()), C.c_void_p(spec.data_ptr()), _stream_ptr()))
         return spec
 
     def blur(self, src, zmap, rp, spec, mode, view=None, weights=None, out=None, first=0, last=0, est=None, est_off=0, sums=None):
+        if self.zx:
+            spec2d, ky = spec
+            _cabi.check(self.lib.mvf_rl_fft_blur_zx(
+                self.plan, C.c_void_p(src.data_ptr()), C.c_void_p(zmap.data_ptr()), int(rp), _cabi.i32x3(self.ksize),
+                C.c_void_p(ky.ctypes.data), C.c_void_p(spec2d.data_ptr()), C.c_void_p(self.real.data_ptr()),
+                C.c_void_p(self.cplx.data_ptr()), int(mode),
+                C.c_void_p(view.data_ptr()) if view is not None else None, dtype_code(view) if view is not None else 0,
+                C.c_void_p(weights.data_ptr()) if weights is not None else None,
+                C.c_void_p(out.data_ptr()) if out is not None else None, int(first), int(last),
+                C.c_void_p(est.data_ptr()) if est is not None else None, int(est_off),
+                C.c_void_p(sums.data_ptr()) if sums is not None else None, _stream_ptr()))
+            return
         _cabi.check(self.lib.mvf_rl_fft_blur(
             self.plan, C.c_void_p(src.data_ptr()), C.c_void_p(zmap.data_ptr()), int(rp), _cabi.i32x3(self.ksize),
             C.c_void_p(spec.data_ptr()), C.c_void_p(self.real.data_ptr()), C.c_void_p(self.cplx.data_ptr()), int(mode),
@@ -103,6 +141,20 @@ class FftBlur:
                 self.plan = None
         except Exception:
             pass
+
+
+def _fft_spectrum(plan, dims, psf, dev):
+    """Convolution state of a view that needs cuFFT: the (z, x) plan when psf = a(y) (x) B(z, x), else the 3-D plan (both
+    created on first use and shared by the views of the plan).  Returns (FftBlur, what its blur() takes as `spec`)."""
+    psf = np.asarray(psf)
+    fy = factor_psf_y(psf)
+    if fy is not None:
+        if getattr(plan, "fft_zx", None) is None:
+            plan.fft_zx = FftBlur(dims, psf.shape, dev, zx=True)
+        return plan.fft_zx, plan.fft_zx.spectrum(fy)
+    if plan.fft is None:
+        plan.fft = FftBlur(dims, psf.shape, dev)
+    return plan.fft, plan.fft.spectrum(psf)
 
 
 def stream_mode():
@@ -201,7 +253,7 @@ class RLPlan:
         self.dims = tuple(int(s) for s in views[0].shape)
         dev = views[0].device
         self.psf_structs, self.zmaps, self.separable, self._keep = [], [], [], []
-        self.radii, self.spectra, self.fft = [], [], None
+        self.radii, self.spectra, self.fft, self.fft_zx, self.fft_of = [], [], None, None, []
         self.dense_mode = os.environ.get("MVF_RL_DENSE", "fft")  # 'fft' (cuFFT) or 'direct' (O(K^3) kernel)
         for p in psfs:
             if any(n < k + 3 for n, k in zip(self.dims, np.asarray(p).shape)):
@@ -209,7 +261,7 @@ class RLPlan:
                                  "needs that much" % (self.dims, np.asarray(p).shape))
             f = None if too_long_for_kernels(p) else factor_psf(p)
             self.separable.append(f is not None)
-            spec = None
+            spec, fobj = None, None
             if f is not None:  # outer-product PSF (axis-aligned view): fused separable kernel
                 self.psf_structs.append(make_psf_struct(f))
                 ksz, rp = len(f[0]), padded_radius(f)
@@ -218,19 +270,16 @@ class RLPlan:
                     raise ValueError("PSF sizes must be odd")
                 self.psf_structs.append(fft_only_psf_struct(p))
                 ksz, rp = int(np.asarray(p).shape[0]), (int(np.asarray(p).shape[0]) - 1) // 2
-                if self.fft is None:
-                    self.fft = FftBlur(self.dims, np.asarray(p).shape, dev)
-                spec = self.fft.spectrum(np.asarray(p))
+                fobj, spec = _fft_spectrum(self, self.dims, p, dev)
             else:              # oblique view: dense PSF -> cuFFT convolution (or the direct kernel on request)
                 st, keep = make_dense_psf_struct(p, dev)
                 self.psf_structs.append(st)
                 self._keep.append(keep)
                 ksz, rp = int(np.asarray(p).shape[0]), (int(keep.shape[0]) - 1) // 2
                 if self.dense_mode == "fft":
-                    if self.fft is None:
-                        self.fft = FftBlur(self.dims, np.asarray(p).shape, dev)
-                    spec = self.fft.spectrum(np.asarray(p))
+                    fobj, spec = _fft_spectrum(self, self.dims, p, dev)
             self.spectra.append(spec)
+            self.fft_of.append(fobj if spec is not None else None)
             self.radii.append(rp)
             self.zmaps.append(torch.from_numpy(zmap_whole(self.dims[0], ksz, rp)).to(dev))
         self.est = torch.empty(self.dims, dtype=torch.float32, device=dev)
@@ -281,9 +330,9 @@ class RLPlan:
         for v in range(self.n):
             last = v == self.n - 1
             if self.spectra[v] is not None:  # cuFFT path
-                self.fft.blur(self.est, self.zmaps[v], self.radii[v], self.spectra[v], 1, view=self.views[v],
+                self.fft_of[v].blur(self.est, self.zmaps[v], self.radii[v], self.spectra[v], 1, view=self.views[v],
                               weights=self.weights[v], out=self.ratio)
-                self.fft.blur(self.ratio, self.zmaps[v], self.radii[v], self.spectra[v], 2, weights=self.weights[v],
+                self.fft_of[v].blur(self.ratio, self.zmaps[v], self.radii[v], self.spectra[v], 2, weights=self.weights[v],
                               out=self.corr, first=1 if v == 0 else 0, last=1 if last else 0, est=self.est,
                               sums=self.sums[1:])
                 continue
@@ -439,33 +488,30 @@ class SlabRLPlan:
             raise ValueError("all views must share one PSF shape")
         kz = next(iter(shapes))[0]
         self.psf_structs, self._keep, self.spectra = [], [], []
-        self.fft = None
+        self.fft, self.fft_zx, self.fft_of = None, None, []
         dense_mode = os.environ.get("MVF_RL_DENSE", "fft")
         rp = None
         facs = []
         for p in psfs:
             f = None if too_long_for_kernels(p) else factor_psf(p)
             facs.append(f)
-            spec = None
+            spec, fobj = None, None
             if f is not None:
                 self.psf_structs.append(make_psf_struct(f))
                 r = padded_radius(f)
             elif too_long_for_kernels(p) and dense_mode == "fft":
                 self.psf_structs.append(fft_only_psf_struct(p))
                 r = (int(np.asarray(p).shape[0]) - 1) // 2
-                if self.fft is None:
-                    self.fft = FftBlur((nzl, ny, nx), np.asarray(p).shape, dev)
-                spec = self.fft.spectrum(np.asarray(p))
+                fobj, spec = _fft_spectrum(self, (nzl, ny, nx), p, dev)
             else:
                 st, keep = make_dense_psf_struct(p, dev)
                 self.psf_structs.append(st)
                 self._keep.append(keep)
                 r = (int(keep.shape[0]) - 1) // 2
                 if dense_mode == "fft":
-                    if self.fft is None:
-                        self.fft = FftBlur((nzl, ny, nx), np.asarray(p).shape, dev)
-                    spec = self.fft.spectrum(np.asarray(p))
+                    fobj, spec = _fft_spectrum(self, (nzl, ny, nx), p, dev)
             self.spectra.append(spec)
+            self.fft_of.append(fobj if spec is not None else None)
             rp = r if rp is None else rp
             if r != rp:
                 raise ValueError("PSFs need one common padded size")
@@ -482,7 +528,7 @@ class SlabRLPlan:
         # isend/irecv (also what the gloo tests on CPU exercise).
         self.symm = None
         want = os.environ.get("MVF_HALO", "symm")
-        if world > 1 and want == "symm" and dev.type == "cuda" and self.fft is None:
+        if world > 1 and want == "symm" and dev.type == "cuda" and self.fft is None and self.fft_zx is None:
             try:
                 self.symm = slab.SymmetricHalo(3, self.halo, ny, nx, dev, group)
             except Exception as e:   # no peer access / no symmetric memory support: the NCCL ring still works
@@ -698,7 +744,7 @@ class SlabRLPlan:
         from . import slab
         if self.spectra[v] is not None:
             slab.exchange_halos_end(pending)
-            self.fft.blur(self.est_pad, self.zmap, self.rp, self.spectra[v], 1, view=self.views[v],
+            self.fft_of[v].blur(self.est_pad, self.zmap, self.rp, self.spectra[v], 1, view=self.views[v],
                           weights=self.weights[v], out=self.ratio)
             return
         if self.streamed[v]:   # the x/y passes of the estimate were done once per (ky, kx) group (xy_estimate)
@@ -733,7 +779,7 @@ class SlabRLPlan:
         last = v == self.n - 1
         if self.spectra[v] is not None:
             slab.exchange_halos_end(pending)
-            self.fft.blur(self.ratio_pad, self.zmap, self.rp, self.spectra[v], 2, weights=self.weights[v], out=self.corr,
+            self.fft_of[v].blur(self.ratio_pad, self.zmap, self.rp, self.spectra[v], 2, weights=self.weights[v], out=self.corr,
                           first=1 if v == 0 else 0, last=1 if last else 0, est=self.est_pad, est_off=self._est_off,
                           sums=self.sums[1:])
             return

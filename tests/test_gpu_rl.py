@@ -322,3 +322,39 @@ def test_rl_unequal_slabs_equal_whole(cuda, kernel, monkeypatch):
         for _ in range(3):
             rl.iterate_emulated(plans)
         assert torch.equal(torch.cat([p.est for p in plans], 0), whole)
+
+
+def test_rl_fft_zx_plan_for_views_rotated_about_y(cuda, monkeypatch):
+    """PSF of a view rotated about y = a(y) (x) B(z, x): batched 2-D (z, x) FFTs + direct y pass (zx plan) against the 3-D
+    FFT plan and the oracle; a PSF rotated about another axis has no such factor and keeps the 3-D plan."""
+    from scipy import ndimage
+    from mvregfus_b200 import fusion, rl, multiview as mv
+    views, params, props, sp = small_case(shape=(48, 40, 52), nviews=3, dtype=np.uint16, seed=13, odd_extra_deg=9.0)
+    tv = [O.transform_stack_dask_numpy(v, p, sp) for v, p in zip(views, params)]
+    w = O.get_weights_simple(props, params, sp)
+    psfs = [mv.get_psf(p, sp, 3, 1) for p in params]
+    assert rl.factor_psf(psfs[1]) is None and rl.factor_psf_y(psfs[1]) is not None
+    a, B = rl.factor_psf_y(psfs[1])
+    assert np.abs(a[None, :, None] * B[:, None, :] - psfs[1]).max() <= 2e-6 * psfs[1].max()
+    dv, dw = [fusion.to_device(v) for v in tv], [fusion.to_device(x) for x in w]
+    ref = O.fuse_LR_with_weights_np(tv, params, sp, num_iterations=3, sz=3, sxy=1, weights=w, return_float=True)
+    plan = rl.RLPlan(dv, dw, psfs)
+    assert plan.fft_zx is not None and plan.fft is None and plan.fft_of[1] is plan.fft_zx
+    got = plan.run(num_iterations=3).cpu().numpy()
+    assert float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0))) <= 1e-3
+    monkeypatch.setenv("MVF_RL_FFT", "3d")
+    plan3 = rl.RLPlan(dv, dw, psfs)
+    assert plan3.fft is not None and plan3.fft_zx is None
+    got3 = plan3.run(num_iterations=3).cpu().numpy()
+    assert float(np.max(np.abs(got - got3) / np.maximum(np.abs(got3), 1.0))) <= 1e-4
+    monkeypatch.delenv("MVF_RL_FFT")
+    # rotated about x instead: y and z mix, no a(y) factor -> 3-D plan; checked against the oracle with explicit PSFs
+    tilted = ndimage.rotate(psfs[0], 11.0, axes=(0, 1), reshape=False, order=1).astype(np.float32)
+    tilted /= tilted.sum()
+    assert rl.factor_psf_y(tilted) is None
+    mixed = [psfs[0], psfs[1], tilted]
+    plan_m = rl.RLPlan(dv, dw, mixed)
+    assert plan_m.fft is not None and plan_m.fft_zx is not None and plan_m.fft_of[2] is plan_m.fft
+    ref_m = O.fuse_LR_with_weights_np(tv, None, sp, num_iterations=3, weights=w, psfs=np.array(mixed), return_float=True)
+    got_m = plan_m.run(num_iterations=3).cpu().numpy()
+    assert float(np.max(np.abs(got_m - ref_m) / np.maximum(np.abs(ref_m), 1.0))) <= 1e-3
