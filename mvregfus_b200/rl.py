@@ -293,14 +293,19 @@ class RLPlan:
                          _vector_aligned(vw, ww, self.est, self.ratio, self.corr)
                          for sep, ps, vw, ww in zip(self.separable, self.psf_structs, views, weights)]
         self.tmp = torch.empty(self.dims, dtype=torch.float32, device=dev) if any(self.streamed) else None
-        self.zz = zz_mode() and all(self.streamed)
+        # v4 schedule for every streamed view; views that need cuFFT (or the fused fallback kernel) keep a ratio volume
+        self.zz = zz_mode() and any(self.streamed)
         if self.zz:   # plane maps of the fused z-ratio-z kernel, side planes for the positions outside the volume
             self.zz_maps = []
-            for ps, rp in zip(self.psf_structs, self.radii):
+            for ps, rp, st in zip(self.psf_structs, self.radii, self.streamed):
+                if not st:
+                    self.zz_maps.append(None)
+                    continue
                 zmap1, rmap, qa, nside = zz_maps_whole(self.dims[0], int(ps.ksize[0]), rp)
                 self.zz_maps.append((np.ascontiguousarray(zmap1), np.ascontiguousarray(rmap), qa, nside))   # host arrays
-            self.side = torch.empty((max(m[3] for m in self.zz_maps),) + self.dims[1:], dtype=torch.float32, device=dev)
-            self.ratio = None   # never materialised
+            self.side = torch.empty((max(m[3] for m in self.zz_maps if m is not None),) + self.dims[1:], dtype=torch.float32, device=dev)
+            if all(self.streamed):
+                self.ratio = None   # never materialised
         # streamed views: (1) the mask (w > 1e-5) of the ratio step is burnt into a copy of the view once, so the ratio
         # pass does not read the weights; (2) views whose PSFs share the in-plane factors (ky, kx) share one x/y pass
         # of the estimate per iteration
@@ -337,7 +342,7 @@ class RLPlan:
                               sums=self.sums[1:])
                 continue
             zm = C.c_void_p(self.zmaps[v].data_ptr())
-            if self.zz:   # side planes, then z + ratio + z in one kernel, then x/y passes + correction epilogue
+            if self.zz and self.streamed[v]:   # side planes, then z + ratio + z in one kernel, then x/y passes + correction epilogue
                 ps = C.byref(self.psf_structs[v])
                 t1 = self.xy_tmps[self.xy_group[v]]
                 zmap1, rmap, qa, nside = self.zz_maps[v]
