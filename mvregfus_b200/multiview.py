@@ -505,10 +505,10 @@ def _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_properties
         else:
             dviews.append(fusion.upload_brick(t.stack, lo, hi))
             windows.append(lo)
-    fused = pipeline.fuse_volume_blockwise(dviews, orig_stack_propertiess, params, stack_properties, windows=windows)
-    if tviews[0].dtype != np.uint16:   # the block loop assembles its result in the dtype of the views
-        fused = fused.to(torch.int32).to(torch.float32)
-    return fusion.to_host(fused)
+    # fused in rows of 128 planes; every row leaves the device (in the dtype of the views, as the block loop assembles its
+    # result) while the next one is being fused
+    return pipeline.fuse_volume_blockwise(dviews, orig_stack_propertiess, params, stack_properties, windows=windows,
+                                          host_dtype=np.uint16 if tviews[0].dtype == np.uint16 else np.float32)
 
 
 def _fuse_blocks_on_device(tviews, params, stack_properties, orig_stack_propertiess, depth, weights_func, fusion_func,

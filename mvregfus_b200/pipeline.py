@@ -40,9 +40,12 @@ def chunk_decisions(data_bits, weight_bits, probe_ok):
     return info
 
 
-def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_properties, chunk=CHUNK, out=None, windows=None):
+def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_properties, chunk=CHUNK, out=None, windows=None,
+                          host_dtype=None):
     """views: list of CUDA tensors (raw views).  Returns the fused uint16 CUDA tensor of stack_properties['size'],
-    equal to what fuse_blockwise(..., weights_func=get_weights_simple, fusion_func=fuse_views_weights) produces."""
+    equal to what fuse_blockwise(..., weights_func=get_weights_simple, fusion_func=fuse_views_weights) produces.
+    host_dtype (uint16 / float32): return a HOST array of that dtype instead (page-locked, pooled): the volume is fused in
+    rows of `chunk` planes and every row leaves the device on a copy stream while the next one is being fused."""
     lib = _cabi.load()
     dims = [int(s) for s in stack_properties["size"]]
     nch = [-(-d // chunk) for d in dims]
@@ -65,9 +68,45 @@ def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_propertie
     info = torch.from_numpy(chunk_decisions(bits[0], bits[1], probe_ok).astype(np.int32)).to(dev)
     if out is None:
         out = torch.empty(dims, dtype=torch.uint16, device=dev)
-    _cabi.check(lib.mvf_fuse_blend_chunked(vs.n, vs.structs, C.c_void_p(out.data_ptr()), _cabi.i32x3(dims),
-                                           _cabi.i32x3((0, 0, 0)), C.c_void_p(info.data_ptr()), chunk, _cabi.i32x3(nch), st))
-    return out
+    if host_dtype is None:
+        _cabi.check(lib.mvf_fuse_blend_chunked(vs.n, vs.structs, C.c_void_p(out.data_ptr()), _cabi.i32x3(dims),
+                                               _cabi.i32x3((0, 0, 0)), C.c_void_p(info.data_ptr()), chunk, _cabi.i32x3(nch), st))
+        return out
+    import weakref
+    host_dtype = np.dtype(host_dtype)
+    tdt = torch.uint16 if host_dtype == np.uint16 else torch.float32
+    raw = fusion._host_buffer(int(np.prod(dims)) * host_dtype.itemsize)
+    hbuf = raw.view(tdt).view(dims)
+    main, copy = torch.cuda.current_stream(), _copy_stream(dev)
+    plane = dims[1] * dims[2]
+    keep = []
+    for z0 in range(0, dims[0], chunk):
+        nzr = min(chunk, dims[0] - z0)
+        _cabi.check(lib.mvf_fuse_blend_chunked(vs.n, vs.structs, C.c_void_p(out.data_ptr() + z0 * plane * 2), _cabi.i32x3((nzr, dims[1], dims[2])),
+                                               _cabi.i32x3((z0, 0, 0)), C.c_void_p(info.data_ptr()), chunk, _cabi.i32x3(nch), st))
+        row = out[z0:z0 + nzr]
+        if tdt != torch.uint16:      # the block loop assembles its result in the dtype of the views
+            row = row.to(torch.int32).to(tdt)
+            keep.append(row)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        copy.wait_event(ev)
+        with torch.cuda.stream(copy):
+            hbuf[z0:z0 + nzr].copy_(row, non_blocking=True)
+    copy.synchronize()
+    arr = hbuf.numpy()
+    weakref.finalize(arr, fusion._host_release, raw)
+    return arr
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    key = str(dev)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
