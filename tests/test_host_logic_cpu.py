@@ -1,0 +1,52 @@
+"""Host-side logic that needs no GPU: PSF factorisations, the overlap-block index arithmetic of the device-resident block
+loop (run here on CPU tensors), work-balanced slab bounds."""
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage
+
+from mvregfus_b200 import multiview as mv
+from mvregfus_b200 import pipeline, rl
+
+
+def _gauss_psf(ksize, sig):
+    f = [np.exp(-0.5 * ((np.arange(k) - (k - 1) / 2) / s) ** 2) for k, s in zip(ksize, sig)]
+    p = f[0][:, None, None] * f[1][None, :, None] * f[2][None, None, :]
+    return (p / p.sum()).astype(np.float32)
+
+
+def test_psf_factorisations():
+    """factor_psf: outer product of three 1-D kernels (axis-aligned view); factor_psf_y: a(y) (x) B(z, x) (view rotated about
+    y, mv:5376-5418); a rotation that mixes y with another axis has neither."""
+    sep = _gauss_psf((19, 19, 19), (6.0, 2.0, 2.0))
+    kz, ky, kx = rl.factor_psf(sep)
+    assert np.abs(kz[:, None, None] * ky[None, :, None] * kx[None, None, :] - sep).max() <= 2e-6 * sep.max()
+    about_y = ndimage.rotate(sep, 7.0, axes=(0, 2), reshape=False, order=1).astype(np.float32)
+    about_y /= about_y.sum()
+    assert rl.factor_psf(about_y) is None
+    a, B = rl.factor_psf_y(about_y)
+    assert a.shape == (19,) and B.shape == (19, 19)
+    assert np.abs(a[None, :, None] * B[:, None, :] - about_y).max() <= 2e-6 * about_y.max()
+    about_x = ndimage.rotate(sep, 7.0, axes=(0, 1), reshape=False, order=1).astype(np.float32)
+    assert rl.factor_psf(about_x) is None and rl.factor_psf_y(about_x) is None
+    long_y = _gauss_psf((9, 45, 9), (2.0, 9.0, 2.0))      # more y taps than the direct pass holds
+    assert rl.factor_psf_y(long_y) is None and rl.too_long_for_kernels(long_y)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+@pytest.mark.parametrize("depth", [0, 5, 20])
+def test_overlap_block_matches_reference_overlap(dtype, depth):
+    """Device-resident overlap blocks (halo from the neighbours, reflection at the volume faces, zeros beyond the volume;
+    overlap_from_sources mv:3662-3707) against the numpy block builder of the host loop, on every chunk of a ragged volume."""
+    rng = np.random.default_rng(3)
+    shape, chunk = (70, 33, 41), 32
+    src = [(rng.random(shape) * 1000).astype(dtype) for _ in range(2)]
+    tsrc = [torch.from_numpy(s.view(np.int16) if dtype == np.uint16 else s) for s in src]
+    if dtype == np.uint16:
+        tsrc = [t.view(torch.uint16) for t in tsrc]
+    nch = [-(-s // chunk) for s in shape]
+    for loc in list(np.ndindex(*nch)) + [(nch[0], 0, 0)]:
+        want = mv._overlap_block(src, loc, depth, chunk)
+        got = pipeline.overlap_block_device(tsrc, loc, depth, chunk)
+        got = got.numpy().view(np.uint16) if dtype == np.uint16 else got.numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), loc
