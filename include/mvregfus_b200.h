@@ -266,6 +266,14 @@ int mvf_background_u16(const uint16_t* in, uint16_t* out, size_t n, uint32_t lev
 int mvf_bin_shrink(const void* in, int dtype, const int32_t in_dims[3], const int32_t factors[3], void* out,
                    void* stream);
 
+/* ---- dual-illumination fusion, plane by plane (illumination_fusion_planewise, mv:391-467) --------------------------
+ * pair: (2, nplanes, n, n) uint16, the two light sheets with the sheet's direction along rows (axis -2) - the layout after
+ * the reference's swapaxes; square planes as the reference requires.  dev_taps: the 2*radius+1 float64 taps of scipy's
+ * gaussian_filter for sigma = n / 50 (device).  scratch: 8 * px + 8 * nplanes * n + 16 * nplanes + 64 bytes, px = nplanes*n*n.
+ * out: (nplanes, n, n) uint16. */
+int mvf_illum_fuse_planes(const uint16_t* pair, int32_t nplanes, int32_t n, const double* dev_taps, int32_t radius,
+                          void* scratch, size_t scratch_bytes, uint16_t* out, void* stream);
+
 /* ---- source brick of a target box: strided host -> device copy ---------------------------------------------
  * view[lo:hi] (zyx, C-contiguous host array of `dims`) -> dense device brick, one cudaMemcpy3DAsync: what a z-slab rank
  * uploads instead of whole views (the per-chunk crop of transform_chunk, mv:1552-1601). */

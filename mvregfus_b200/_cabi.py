@@ -25,7 +25,7 @@ EXPORTS = (
     "mvf_rl_fft_padded_dims", "mvf_rl_fft_plan_create", "mvf_rl_fft_plan_set_workspace", "mvf_rl_fft_plan_destroy",
     "mvf_rl_fft_psf_spectrum", "mvf_rl_fft_blur", "mvf_rl_fft_plan_create_zx", "mvf_rl_fft_plan_padded", "mvf_rl_fft_blur_zx",
     "mvf_rl_stream_supported", "mvf_rl_xy", "mvf_rl_blur_z", "mvf_rl_ratio_z", "mvf_rl_correct_z",
-    "mvf_rl_zz", "mvf_rl_xy_correct", "mvf_copy_brick_h2d",
+    "mvf_rl_zz", "mvf_rl_xy_correct", "mvf_copy_brick_h2d", "mvf_illum_fuse_planes",
     "mvf_subsample", "mvf_range_u16", "mvf_hist_u16", "mvf_background_u16", "mvf_bin_shrink",
 )
 MVF_RL_KMAX = 43
@@ -117,6 +117,8 @@ def _declare(lib):
     lib.mvf_range_u16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.mvf_hist_u16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mvf_background_u16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.mvf_illum_fuse_planes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p,
+                                          C.c_void_p]
     lib.mvf_copy_brick_h2d.argtypes = [C.c_void_p, C.c_int, i32p, i32p, i32p, C.c_void_p, C.c_void_p]
     lib.mvf_bin_shrink.argtypes = [C.c_void_p, C.c_int, i32p, i32p, C.c_void_p, C.c_void_p]
     for name in EXPORTS:

@@ -286,3 +286,136 @@ extern "C" int mvf_copy_brick_h2d(const void* host, int dtype, const int32_t dim
   MVF_CUDA(cudaMemcpy3DAsync(&p, as_stream(stream)));
   return MVF_OK;
 }
+
+// ---- dual-illumination fusion, plane by plane (illumination_fusion_planewise, mv:391-467) ------------------------------
+// pair: (2, P, n, n) uint16 - both light sheets, planes already oriented so that the sheet travels along rows (axis -2).
+//   mask = log(I0 + I1 - min(I0, I1 over the plane pair)), rescaled to [0, 1] with the plane's own extremes      (float64)
+//   total[x] = sum_y mask ; rows whose index r has total[r] == 0 are set to 1 (the reference selects ROWS with the per-column
+//   total - square planes), total == 0 -> n ; right[y][x] = cumsum_y(mask)[y][x] > total[y] / 2 (its transposes broadcast the
+//   per-column total along the row index as well)                                                                  (0 / 1)
+//   right = gaussian_filter(float32(right), sigma = n / 50 per axis)   (scipy: reflect, radius int(4 sigma + .5), per-axis
+//   passes in float64 with a float32 result each; taps from the host, accumulated centre first, then pairs from far to near)
+//   out = uint16(I0 * (1 - right) + I1 * right)                                                                  (float32)
+namespace mvf {
+
+struct IllumStats { unsigned m, smin, smax, pad; };
+
+__global__ void __launch_bounds__(256) illum_stats_kernel(const uint16_t* __restrict__ pair, size_t plane, size_t pstride2, IllumStats* stats) {
+  const uint16_t* p0 = pair + (size_t)blockIdx.x * plane;
+  const uint16_t* p1 = p0 + pstride2;
+  unsigned m = 0xFFFFFFFFu, smin = 0xFFFFFFFFu, smax = 0u;
+  for (size_t i = threadIdx.x; i < plane; i += 256) {
+    const unsigned a = p0[i], b = p1[i];
+    m = min(m, min(a, b));
+    smin = min(smin, a + b);
+    smax = max(smax, a + b);
+  }
+  __shared__ unsigned sm[3][8];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    m = min(m, __shfl_xor_sync(0xffffffffu, m, s));
+    smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, s));
+    smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, s));
+  }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = m; sm[1][threadIdx.x >> 5] = smin; sm[2][threadIdx.x >> 5] = smax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { m = min(m, sm[0][w]); smin = min(smin, sm[1][w]); smax = max(smax, sm[2][w]); }
+    stats[blockIdx.x] = IllumStats{m, smin, smax, 0u};
+  }
+}
+
+__device__ __forceinline__ double illum_mask(unsigned s, unsigned m, double lmin, double inv_den_num) {
+  // (log(s - m) - lmin) / (lmax - lmin): the division is done by the caller's denominator, as numpy does it
+  return __ddiv_rn(__dsub_rn(log((double)(s - m)), lmin), inv_den_num);
+}
+
+// thread = column x of plane p.  PASS 0: total[p][x].  PASS 1: right[p][y][x] (needs every total of the plane).
+template <int PASS>
+__global__ void __launch_bounds__(128) illum_columns_kernel(const uint16_t* __restrict__ pair, int n, size_t pstride2,
+                                                            const IllumStats* __restrict__ stats, double* total, float* right) {
+  const int x = blockIdx.x * 128 + threadIdx.x, p = blockIdx.y;
+  if (x >= n) return;
+  const size_t plane = (size_t)n * n;
+  const uint16_t* p0 = pair + (size_t)p * plane + x;
+  const uint16_t* p1 = p0 + pstride2;
+  const IllumStats st = stats[p];
+  const double lmin = log((double)(st.smin - st.m)), lmax = log((double)(st.smax - st.m));
+  const double den = __dsub_rn(lmax, lmin);
+  double* tot = total + (size_t)p * n;
+  if (PASS == 0) {
+    double acc = 0.0;
+    for (int y = 0; y < n; ++y) acc = __dadd_rn(acc, illum_mask((unsigned)p0[(size_t)y * n] + p1[(size_t)y * n], st.m, lmin, den));
+    tot[x] = acc;
+  } else {
+    // (cumsum.T > total.T / 2).T broadcasts the per-column total along the ROW index: the threshold of row y is total[y] / 2
+    float* r = right + (size_t)p * plane + x;
+    double cum = 0.0;
+    for (int y = 0; y < n; ++y) {
+      const double traw = tot[y];
+      const double mv = traw == 0.0 ? 1.0 : illum_mask((unsigned)p0[(size_t)y * n] + p1[(size_t)y * n], st.m, lmin, den);
+      cum = __dadd_rn(cum, mv);
+      r[(size_t)y * n] = cum > __ddiv_rn(traw == 0.0 ? (double)n : traw, 2.0) ? 1.f : 0.f;
+    }
+  }
+}
+
+// one Gaussian pass along AXIS (0: rows / y, 1: columns / x) of every plane; scipy's 'reflect' extension (edge repeated)
+template <int AXIS>
+__global__ void __launch_bounds__(256) illum_gauss_kernel(const float* __restrict__ in, float* __restrict__ out, int n, size_t total_px,
+                                                          const double* __restrict__ w, int r) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total_px) return;
+  const int x = (int)(i % n), y = (int)((i / n) % n);
+  const int c = AXIS == 0 ? y : x;
+  const float* base = in + (i - (AXIS == 0 ? (size_t)y * n : (size_t)x));
+  const size_t stride = AXIS == 0 ? (size_t)n : 1;
+  auto at = [&](int q) {
+    q = q < 0 ? -q - 1 : (q >= n ? 2 * n - 1 - q : q);
+    return (double)base[(size_t)q * stride];
+  };
+  double tmp = __dmul_rn(at(c), w[r]);
+  for (int ii = -r; ii < 0; ++ii) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(c + ii), at(c - ii)), w[ii + r]));
+  out[i] = (float)tmp;
+}
+
+__global__ void __launch_bounds__(256) illum_blend_kernel(const uint16_t* __restrict__ pair, size_t pstride2, const float* __restrict__ right,
+                                                          uint16_t* __restrict__ out, size_t total_px) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total_px) return;
+  const float rw = right[i];
+  const float a = __fmul_rn((float)pair[i], __fsub_rn(1.f, rw)), b = __fmul_rn((float)pair[i + pstride2], rw);
+  out[i] = (uint16_t)__fadd_rn(a, b);
+}
+
+}  // namespace mvf
+
+extern "C" int mvf_illum_fuse_planes(const uint16_t* pair, int32_t nplanes, int32_t n, const double* dev_taps, int32_t radius,
+                                     void* scratch, size_t scratch_bytes, uint16_t* out, void* stream) {
+  MVF_CHECK_ARG(pair && dev_taps && scratch && out, "NULL argument");
+  MVF_CHECK_ARG(nplanes > 0 && nplanes <= 65535 && n > 1 && radius >= 0 && radius < n, "bad plane count, extent or radius");
+  const size_t plane = (size_t)n * n, px = plane * nplanes;
+  const size_t need = px * 4 * 2 + (size_t)nplanes * n * 8 + (size_t)nplanes * sizeof(IllumStats) + 64;
+  MVF_CHECK_ARG(scratch_bytes >= need, "scratch too small (2 float planes per input plane + n doubles + 16 bytes per plane + 64)");
+  cudaStream_t st = as_stream(stream);
+  char* sp = static_cast<char*>(scratch);
+  float* right = reinterpret_cast<float*>(sp);
+  float* tmp = right + px;
+  double* total = reinterpret_cast<double*>(tmp + px);
+  IllumStats* stats = reinterpret_cast<IllumStats*>(total + (size_t)nplanes * n);
+  illum_stats_kernel<<<nplanes, 256, 0, st>>>(pair, plane, px, stats);
+  MVF_LAUNCHED();
+  dim3 cg((n + 127) / 128, nplanes);
+  illum_columns_kernel<0><<<cg, 128, 0, st>>>(pair, n, px, stats, total, right);
+  MVF_LAUNCHED();
+  illum_columns_kernel<1><<<cg, 128, 0, st>>>(pair, n, px, stats, total, right);
+  MVF_LAUNCHED();
+  const unsigned gb = (unsigned)((px + 255) / 256);
+  illum_gauss_kernel<0><<<gb, 256, 0, st>>>(right, tmp, n, px, dev_taps, radius);
+  MVF_LAUNCHED();
+  illum_gauss_kernel<1><<<gb, 256, 0, st>>>(tmp, right, n, px, dev_taps, radius);
+  MVF_LAUNCHED();
+  illum_blend_kernel<<<gb, 256, 0, st>>>(pair, px, right, out, px);
+  MVF_LAUNCHED();
+  return MVF_OK;
+}

@@ -7,6 +7,7 @@ Drop-in counterparts, same names and argument meaning as the reference:
                                                            subsampling + np.histogram(data, 256) per level
   * ``subtract_background(stack, background_level)``       mvregfus/multiview.py:316
   * ``bin_stack(im, bin_factors)``                         mvregfus/mv_utils.py:288-311 (sitk.BinShrink)
+  * ``illumination_fusion_planewise(stack, fusion_axis)``  mvregfus/multiview.py:391-467
 numpy / ImageArray in, numpy / ImageArray out; device tensors are accepted and then returned as tensors.
 The kernels live in csrc/prepost.cu behind the C-ABI; there is no CPU fallback.
 """
@@ -109,3 +110,43 @@ def bin_stack(im, bin_factors=np.array([1, 1, 1])):
     _cabi.check(_cabi.load().mvf_bin_shrink(C.c_void_p(d.data_ptr()), dtype_code(d), _cabi.i32x3(dims), _cabi.i32x3(f_zyx),
                                             C.c_void_p(out.data_ptr()), _stream_ptr()))
     return ImageArray(out.cpu().numpy(), spacing=binned_spacing, origin=binned_origin, rotation=rotation)
+
+
+def gaussian_taps(sigma, truncate=4.0):
+    """Taps and radius of scipy.ndimage.gaussian_filter1d (order 0): exp(-x^2 / (2 sigma^2)) on [-r, r], r = int(truncate *
+    sigma + 0.5), normalised - the same float64 expressions as scipy's _gaussian_kernel1d."""
+    sigma = float(sigma)
+    radius = int(truncate * sigma + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum(), radius
+
+
+def illumination_fusion_planewise(stack, fusion_axis=2):
+    """Fusion of the two light-sheet illuminations of a view, plane by plane (mv:391-467): ``stack`` (2, z, y, x) uint16 ->
+    (z, ., .) uint16.  Same contract as the reference, quirks included: planes (after swapping ``fusion_axis`` with the last
+    axis) must be square, and the swap back is applied with the same axis number to the 3-D result (a no-op for the default
+    2: the planes come back transposed)."""
+    was_tensor = isinstance(stack, torch.Tensor)
+    arr = stack if was_tensor else np.asarray(stack)
+    if arr.ndim != 4 or arr.shape[0] != 2:
+        raise ValueError("illumination_fusion_planewise expects a (2, z, y, x) stack")
+    if (arr.dtype if not was_tensor else None) not in (None, np.dtype(np.uint16)) or (was_tensor and arr.dtype != torch.uint16):
+        raise TypeError("illumination_fusion_planewise fuses uint16 stacks")
+    d = arr if was_tensor else to_device(np.ascontiguousarray(arr))
+    pair = d.view(torch.int16).swapaxes(fusion_axis, -1).contiguous().view(torch.uint16)
+    nplanes, n0, n1 = (int(s) for s in pair.shape[1:])
+    if n0 != n1:   # the reference indexes the rows of the (n0, n1) mask with a boolean of length n1
+        raise IndexError("boolean index did not match indexed array along axis 0; size of axis is %d but size of "
+                         "corresponding boolean axis is %d" % (n0, n1))
+    taps, radius = gaussian_taps(n0 / 100 * 2.)
+    dtaps = torch.from_numpy(taps).to(pair.device)
+    px = nplanes * n0 * n0
+    nbytes = 8 * px + 8 * nplanes * n0 + 16 * nplanes + 64
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=pair.device)
+    out = torch.empty((nplanes, n0, n0), dtype=torch.uint16, device=pair.device)
+    _cabi.check(_cabi.load().mvf_illum_fuse_planes(C.c_void_p(pair.data_ptr()), nplanes, n0, C.c_void_p(dtaps.data_ptr()), radius,
+                                                   C.c_void_p(scratch.data_ptr()), nbytes, C.c_void_p(out.data_ptr()), _stream_ptr()))
+    if was_tensor:
+        return out.view(torch.int16).swapaxes(fusion_axis, -1).contiguous().view(torch.uint16)
+    return np.swapaxes(out.cpu().numpy(), fusion_axis, -1)

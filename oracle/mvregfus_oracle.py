@@ -770,3 +770,30 @@ def bin_stack(im, bin_factors=np.array([1, 1, 1])):
     binned_origin = im.origin + (binned_spacing - im.spacing) / 2.
     out = bin_shrink(np.asarray(im), [int(i) for i in bin_factors][::-1])
     return ImageArray(out, spacing=binned_spacing, origin=binned_origin, rotation=im.rotation)
+
+
+def illumination_fusion_planewise(stack, fusion_axis=2):
+    """Dual-illumination fusion, plane by plane (mv:391-467).  ``stack``: (2, z, y, x) uint16, the two light sheets.
+
+    Per plane (after swapping ``fusion_axis`` with the last axis of the 4-D pair): mask = log(I0 + I1 - min), rescaled to
+    [0, 1]; the column-wise cumulative sum of the mask decides where the second illumination takes over (past half of the
+    column total); that binary map is smoothed with a Gaussian of sigma = plane shape / 50 and blends the two planes.
+    Quirks kept: rows are selected with the per-COLUMN total (``mask[total == 0] = True``) and the transposes of the
+    threshold test broadcast that total along the row index as well (square planes only); the swap
+    back uses the same axis number on the 3-D result, a no-op for the default 2 - the planes come back transposed."""
+    from scipy import ndimage
+    stack = np.swapaxes(np.array(stack), fusion_axis, -1)
+    out = np.empty(stack.shape[1:], dtype=np.uint16)
+    for p in range(stack.shape[1]):
+        planes = stack[:, p]
+        mask = np.log(np.sum(planes, 0) - planes.min())
+        mask = (mask - mask.min()) / (mask.max() - mask.min())
+        total = np.sum(mask, axis=-2)
+        mask[total == 0] = True
+        total[total == 0] = mask.shape[1]
+        cumsum = np.cumsum(mask, axis=-2)
+        right_weight = (cumsum.T > total.T / 2.).T
+        kernel = np.array(mask.shape) / 100 * 2.
+        right_weight = ndimage.gaussian_filter(right_weight.astype(np.float32), kernel)
+        out[p] = (planes[0] * (1 - right_weight) + planes[1] * right_weight).astype(np.uint16)
+    return np.swapaxes(out, fusion_axis, -1)

@@ -156,6 +156,17 @@ def map_blocks(func, *args, dtype=None, chunks=None, drop_axis=None, **kwargs):
                           "chunk-location": tuple(loc), "num-chunks": first.numblocks, "dtype": dtype}
             kw["block_info"] = info
         blocks[loc] = np.asarray(func(*call_args, **kw))
+    if drop_axis is not None:   # the function removes these axes from every block (one chunk along them): drop them from the grid
+        drop = sorted([drop_axis] if np.isscalar(drop_axis) else list(drop_axis))
+        assert all(first.numblocks[d] == 1 for d in drop)
+        blocks = {tuple(i for d, i in enumerate(loc) if d not in drop): b for loc, b in blocks.items()}
+        grid = tuple(g for d, g in enumerate(first.numblocks) if d not in drop)
+        sample = blocks[(0,) * len(grid)]
+        assert all(b.shape == sample.shape for b in blocks.values())
+        out = np.empty(tuple(g * s for g, s in zip(grid, sample.shape)), dtype=sample.dtype)
+        for loc, b in blocks.items():
+            out[tuple(slice(i * s, (i + 1) * s) for i, s in zip(loc, sample.shape))] = b
+        return EagerArray(out, sample.shape)
     # assemble like dask's concatenate3: dtype of the FIRST block, blocks written in place
     sample = blocks[(0,) * len(first.numblocks)]
     bshape = sample.shape
@@ -345,6 +356,24 @@ def main():
                                 mv.get_weights_simple, ff, {}, dict(fkw), block_info=info)
             out["block_%s_%s" % (tag, ftag)] = np.asarray(res)
     out["block_tviews"], out["block_params"] = tv, params
+
+    # ---- G9: dual-illumination fusion (mv:391-467, run unmodified through the eager map_blocks) ------
+    import contextlib
+    import io
+    rng = np.random.default_rng(77)
+    z, y, x = np.mgrid[:6, :44, :44]
+    base = 220 + 180 * np.abs(np.sin((x + 2 * y + 5 * z) / 23.0)) * np.sin((y + 3) / 50.0 * np.pi) ** 2
+    # fusion_axis counts axes of the (2, z, y, x) pair; only the default 2 runs: planes must be square (the reference indexes
+    # rows with a per-column mask) and its final swap-back applies the same axis number to the 3-D result, where it is a
+    # no-op for 2 (the planes come back transposed) and out of range for 3
+    for tag, seed in (("a", 0), ("b", 1)):
+        ramp = y / 43.0
+        left = base * (0.35 + 0.65 * ramp) + rng.random(base.shape) * 12
+        right = base * (1.0 - 0.65 * ramp) + rng.random(base.shape) * (12 + 30 * seed)
+        pair = np.array([left, right]).astype(np.uint16)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fused = mv.illumination_fusion_planewise(pair.copy(), fusion_axis=2)
+        out["illum_%s_in" % tag], out["illum_%s_out" % tag] = pair, np.asarray(fused)
 
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)

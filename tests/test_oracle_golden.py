@@ -155,3 +155,11 @@ def test_fuse_block_control_flow(tag, ftag):
         ff, kw = O.fuse_LR_with_weights_np, {"num_iterations": 2, "sz": 2, "sxy": 1, "tol": 5e-5}
     res = O.fuse_block(tv, None, G["block_params"], spb, props, (0, 0, 0), 4, "blending", ff, kw, chunk=32)
     assert np.array_equal(np.asarray(res), G["block_%s_%s" % (tag, ftag)])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_illumination_fusion_bit_exact(tag):
+    """mv:391-467 run unmodified (eager map_blocks stand-in) vs the oracle's restatement."""
+    got = O.illumination_fusion_planewise(G["illum_%s_in" % tag], fusion_axis=2)
+    ref = G["illum_%s_out" % tag]
+    assert got.dtype == ref.dtype and got.shape == ref.shape and np.array_equal(got, ref)

@@ -110,3 +110,32 @@ def test_gpu_vectorised_x2_paths_match_oracle(cuda):
     im = ImageArray(vol)
     for fac in ([2, 2, 1], [2, 1, 3], [2, 4, 2]):   # x, y, z
         assert np.array_equal(np.asarray(prepost.bin_stack(im, np.array(fac))), np.asarray(O.bin_stack(im, np.array(fac))))
+
+
+@pytest.mark.gpu
+def test_gpu_illumination_fusion_matches_reference(cuda):
+    """illumination_fusion_planewise (mv:391-467) on the device: the reference's own outputs (run unmodified for the golden
+    file), a larger case against the oracle, tensor in / tensor out, and the reference's square-plane requirement."""
+    import torch
+    from mvregfus_b200 import prepost
+    GR = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
+    for tag in ("a", "b"):
+        got = prepost.illumination_fusion_planewise(GR["illum_%s_in" % tag], fusion_axis=2)
+        ref = GR["illum_%s_out" % tag]
+        assert got.dtype == np.uint16 and got.shape == ref.shape
+        d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+        assert d.max() <= 1 and np.mean(d > 0) <= 1e-3, (d.max(), np.mean(d > 0))
+    rng = np.random.default_rng(5)
+    z, y, x = np.mgrid[:5, :160, :160]
+    base = 300 + 2500 * np.abs(np.sin((x + y) / 37.0)) * np.sin((y + 1) / 170.0 * np.pi) ** 2
+    pair = np.array([base * (0.2 + 0.8 * y / 159.0) + rng.random(base.shape) * 40,
+                     base * (1.0 - 0.8 * y / 159.0) + rng.random(base.shape) * 40]).astype(np.uint16)
+    pair[:, 2, :, 70:90] = 310            # a flat band: columns with (nearly) constant mask
+    ref = O.illumination_fusion_planewise(pair, fusion_axis=2)
+    got = prepost.illumination_fusion_planewise(pair, fusion_axis=2)
+    d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 1 and np.mean(d > 0) <= 1e-3, (d.max(), np.mean(d > 0))
+    t = prepost.illumination_fusion_planewise(torch.from_numpy(pair.view(np.int16)).cuda().view(torch.uint16), fusion_axis=2)
+    assert isinstance(t, torch.Tensor) and np.array_equal(t.cpu().numpy(), got)
+    with pytest.raises(IndexError):
+        prepost.illumination_fusion_planewise(pair[:, :, :100, :], fusion_axis=2)
