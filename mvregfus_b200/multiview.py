@@ -489,6 +489,14 @@ def _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_properties
             return None
     if len(tviews) > 8 or len({t.dtype for t in tviews}) != 1:
         return None
+    host_dtype = np.uint16 if tviews[0].dtype == np.uint16 else np.float32
+    if os.environ.get("MVF_ROW_STREAM", "1") != "0" and os.environ.get("MVF_BRICK_UPLOAD", "1") != "0":
+        # volumes of several 128-plane rows: per-row source bricks on an upload stream one row ahead of the kernels, results
+        # on a download stream - both PCIe directions busy at once
+        fused = pipeline.fuse_volume_rows_from_host([t.stack for t in tviews], orig_stack_propertiess, params, stack_properties,
+                                                    host_dtype)
+        if fused is not None:
+            return fused
     # Upload per view only the source brick the target box touches (the reference's per-chunk crop, mv:1552-1601): for a
     # z-slab of the fused frame that is a fraction of every view; whole views go up in one piece.
     from . import slab
@@ -508,7 +516,7 @@ def _fuse_lazy_on_device(tviews, params, stack_properties, orig_stack_properties
     # fused in rows of 128 planes; every row leaves the device (in the dtype of the views, as the block loop assembles its
     # result) while the next one is being fused
     return pipeline.fuse_volume_blockwise(dviews, orig_stack_propertiess, params, stack_properties, windows=windows,
-                                          host_dtype=np.uint16 if tviews[0].dtype == np.uint16 else np.float32)
+                                          host_dtype=host_dtype)
 
 
 def _fuse_blocks_on_device(tviews, params, stack_properties, orig_stack_propertiess, depth, weights_func, fusion_func,

@@ -102,8 +102,8 @@ def fuse_volume_blockwise(views, orig_stack_propertiess, params, stack_propertie
 _COPY_STREAMS = {}
 
 
-def _copy_stream(dev):
-    key = str(dev)
+def _copy_stream(dev, role="d2h"):
+    key = (str(dev), role)
     if key not in _COPY_STREAMS:
         _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _COPY_STREAMS[key]
@@ -230,3 +230,101 @@ def fuse_blocks_device(tviews, params, stack_properties, orig_stack_propertiess,
     res = res.contiguous()
     return res.view(torch.uint16) if vdtype == torch.uint16 else res
 
+
+
+def fuse_volume_rows_from_host(host_views, orig_stack_propertiess, params, stack_properties, host_dtype, chunk=CHUNK):
+    """fuse_volume_blockwise with the views still in HOST memory: the fused volume is produced in rows of `chunk` planes, and
+    for every row only the source brick it touches is uploaded per view (the reference's per-chunk crop, mv:1552-1601) - on
+    an upload stream that runs one row ahead, while the previous row's result leaves the device on a download stream.  Uploads,
+    kernels and downloads of consecutive rows overlap in both PCIe directions; the decisions per chunk are the same as in the
+    whole-volume launch.  Returns a host array (page-locked, pooled), or None when the rows' bricks overlap so much that
+    whole views are cheaper to send (the caller then uploads them once)."""
+    import weakref
+    from . import slab
+    lib = _cabi.load()
+    dims = [int(s) for s in stack_properties["size"]]
+    nch = [-(-d // chunk) for d in dims]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nv = len(host_views)
+    sp = np.asarray(stack_properties["spacing"], dtype=np.float64)
+    rows = [(z0, min(chunk, dims[0] - z0)) for z0 in range(0, dims[0], chunk)]
+    if len(rows) < 2:
+        return None
+    # source brick of every (row, view)
+    bricks, total = [], 0
+    for z0, nzr in rows:
+        per_view = []
+        for v in range(nv):
+            osp = orig_stack_propertiess[v]
+            vshape = np.asarray(np.asarray(host_views[v]).shape)
+            matrix, offset = fusion.index_space_affine(params[v], np.asarray(osp["spacing"], dtype=np.float64),
+                                                       np.asarray(osp["origin"], dtype=np.float64), sp,
+                                                       np.asarray(stack_properties["origin"], dtype=np.float64))
+            lo, hi = slab.source_brick(matrix, offset, vshape, z0, z0 + nzr, dims[1], dims[2])
+            lo = np.minimum(lo, vshape - 1)
+            hi = np.maximum(hi, lo + 1)
+            per_view.append((lo, hi))
+            total += int(np.prod(hi - lo)) * np.asarray(host_views[v]).dtype.itemsize
+        bricks.append(per_view)
+    if total > 1.25 * sum(np.asarray(h).nbytes for h in host_views):
+        return None
+    host_dtype = np.dtype(host_dtype)
+    tdt = torch.uint16 if host_dtype == np.uint16 else torch.float32
+    raw = fusion._host_buffer(int(np.prod(dims)) * host_dtype.itemsize)
+    hbuf = raw.view(tdt).view(dims)
+    main, up, down = torch.cuda.current_stream(), _copy_stream(dev, "h2d"), _copy_stream(dev, "d2h")
+    per_row = nch[1] * nch[2]
+    flags = torch.zeros((2, int(np.prod(nch))), dtype=torch.int32, device=dev)
+    info = torch.zeros(int(np.prod(nch)), dtype=torch.int32, device=dev)
+    out = torch.empty(dims, dtype=torch.uint16, device=dev)
+    plane = dims[1] * dims[2]
+    keep, uploaded = [], {}
+
+    def upload(k):
+        if k == 0:
+            up.wait_stream(main)
+        with torch.cuda.stream(up):
+            tensors = [fusion.upload_brick(host_views[v], lo, hi, device=dev) for v, (lo, hi) in enumerate(bricks[k])]
+            ev = torch.cuda.Event()
+            ev.record(up)
+        uploaded[k] = (tensors, ev)
+        keep.extend(tensors)
+
+    upload(0)
+    # (host work while the first bricks travel) probe-point early-out of get_weights_simple on every 128^3 block (float64; mv:3491-3532)
+    locs = np.array(list(np.ndindex(*nch)), dtype=np.float64)
+    origins = np.asarray(stack_properties["origin"], dtype=np.float64) + locs * chunk * sp
+    probe_ok = np.stack([probe_any_inside_blocks(orig_stack_propertiess[v], params[v], origins, [chunk] * 3, sp, 5)
+                         for v in range(nv)], axis=1)
+    for k, (z0, nzr) in enumerate(rows):
+        if k + 1 < len(rows):
+            upload(k + 1)
+        tensors, ev = uploaded.pop(k)
+        main.wait_event(ev)
+        vs = fusion.build_viewset(tensors, orig_stack_propertiess, params, stack_properties, weights="blending", probe=False,
+                                  windows=[lo for lo, _ in bricks[k]])
+        keep.append(vs)
+        st = fusion._stream_ptr()
+        rdims, rorg = _cabi.i32x3((nzr, dims[1], dims[2])), _cabi.i32x3((z0, 0, 0))
+        for probe in (0, 1):
+            _cabi.check(lib.mvf_chunk_probe(vs.n, vs.structs, probe, rdims, rorg, C.c_void_p(flags[probe].data_ptr()), chunk,
+                                            _cabi.i32x3(nch), st))
+        sl = slice(k * per_row, (k + 1) * per_row)
+        bits = flags[:, sl].cpu().numpy().astype(np.uint32)        # waits for this row's uploads and probes only
+        info[sl] = torch.from_numpy(chunk_decisions(bits[0], bits[1], probe_ok[sl]).astype(np.int32)).to(dev)
+        _cabi.check(lib.mvf_fuse_blend_chunked(vs.n, vs.structs, C.c_void_p(out.data_ptr() + z0 * plane * 2), rdims, rorg,
+                                               C.c_void_p(info.data_ptr()), chunk, _cabi.i32x3(nch), st))
+        row = out[z0:z0 + nzr]
+        if tdt != torch.uint16:      # the block loop assembles its result in the dtype of the views
+            row = row.to(torch.int32).to(tdt)
+            keep.append(row)
+        evk = torch.cuda.Event()
+        evk.record(main)
+        down.wait_event(evk)
+        with torch.cuda.stream(down):
+            hbuf[z0:z0 + nzr].copy_(row, non_blocking=True)
+    down.synchronize()
+    main.synchronize()
+    arr = hbuf.numpy()
+    weakref.finalize(arr, fusion._host_release, raw)
+    return arr

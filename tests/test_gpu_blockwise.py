@@ -154,3 +154,34 @@ def test_slab_box_uploads_source_bricks_only(cuda, dtype, monkeypatch):
     ref = np.asarray(O.fuse_blockwise(tvo, params, sp_slab, props, fusion_block_overlap=0))
     d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
     assert d.max() <= 3 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+def test_row_streamed_socket_equals_whole_upload(cuda, dtype, monkeypatch):
+    """Volumes of several 128-plane rows through the drop-in socket: per-row source bricks on an upload stream one row
+    ahead, kernels, results on a download stream (pipeline.fuse_volume_rows_from_host).  Bit for bit the result of the
+    whole-view upload + one launch, and the oracle's block loop within the usual integer tolerance."""
+    from mvregfus_b200 import multiview as mv, pipeline, synthetic
+    from mvregfus_b200.image_array import ImageArray
+    shape = (150, 40, 150)
+    views, params, props = synthetic.make_views(shape, 4, dtype=dtype, seed=31)
+    views[2][:, :, 100:] = 0          # a view without signal in part of the volume: per-chunk decisions differ between rows
+    views = [ImageArray(v, spacing=p["spacing"], origin=p["origin"]) for v, p in zip(views, props)]
+    sp = mv.calc_stack_properties_from_views_and_params(props, params, spacing=[1.0] * 3)
+    assert int(sp["size"][0]) > 128
+    used = []
+    real = pipeline.fuse_volume_rows_from_host
+    monkeypatch.setattr(pipeline, "fuse_volume_rows_from_host", lambda *a, **k: (used.append(1), real(*a, **k))[1])
+
+    def run():
+        tv = [mv.transform_stack_dask_numpy(v, p, stack_properties=sp) for v, p in zip(views, params)]
+        return np.asarray(mv.fuse_blockwise_arrays(tv, params, sp, props))
+    got = run()
+    assert used == [1]
+    monkeypatch.setenv("MVF_ROW_STREAM", "0")
+    whole = run()
+    assert used == [1] and got.dtype == whole.dtype == dtype and np.array_equal(got, whole)
+    tvo = [O.transform_stack_dask_numpy(v, p, sp) for v, p in zip(views, params)]
+    ref = np.asarray(O.fuse_blockwise(tvo, params, sp, props, fusion_block_overlap=0))
+    d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 3 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
