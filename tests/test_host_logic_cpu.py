@@ -50,3 +50,31 @@ def test_overlap_block_matches_reference_overlap(dtype, depth):
         got = pipeline.overlap_block_device(tsrc, loc, depth, chunk)
         got = got.numpy().view(np.uint16) if dtype == np.uint16 else got.numpy()
         assert got.shape == want.shape and np.array_equal(got, want), loc
+
+
+def test_gaussian_taps_are_scipys():
+    """prepost.gaussian_taps restates scipy's _gaussian_kernel1d: filtering a delta must return exactly these taps."""
+    from mvregfus_b200 import prepost
+    for sigma in (0.88, 3.2, 20.48):
+        taps, r = prepost.gaussian_taps(sigma)
+        delta = np.zeros(4 * r + 1)
+        delta[2 * r] = 1.0
+        resp = ndimage.gaussian_filter1d(delta, sigma, mode="constant")
+        assert r == int(4.0 * sigma + 0.5) and np.array_equal(resp[r:3 * r + 1], taps)
+
+
+def test_chunk_decisions_follow_fuse_block():
+    """Per-chunk decision words of the one-launch block loop (mv:3826-3909): bits 0-7 views taking part, bit 8 copy mode,
+    bits 12-15 the view whose transformed voxels are copied."""
+    data = np.array([0b000, 0b010, 0b111, 0b111, 0b110, 0b011], dtype=np.uint32)
+    wbits = np.array([0b000, 0b010, 0b111, 0b100, 0b000, 0b011], dtype=np.uint32)
+    probe = np.ones((6, 3), dtype=bool)
+    probe[5, 0] = False            # probe-point early-out drops view 0 of the last chunk
+    info = pipeline.chunk_decisions(data, wbits, probe)
+    copy = lambda v: (1 << 8) | (v << 12)
+    assert list(info) == [copy(0),   # no live view: tviews_block[0]
+                          copy(1),   # one live view: raw copy of it
+                          0b111,     # three weighted views: fuse them
+                          copy(2),   # only view 2 has weight: copy it
+                          copy(1),   # no weighted view: first live view
+                          copy(1)]   # views 0 and 1 live, view 0 dropped by the probe: copy view 1
