@@ -9,7 +9,9 @@ additive fusion).  Rank 0 prints ONE JSON line (contract in the task description
   value        fused voxels / s with the views already resident in HBM (CUDA events, max over ranks)
   e2e          the same metric through the drop-in entry points of mvregfus_b200.multiview with HOST numpy buffers:
                transform_stack_dask_numpy per view + fuse_blockwise_arrays (the reference's fuse_blockwise socket,
-               mv:3637-3916), host->device and device->host copies inside the timed region
+               mv:3637-3916), host->device and device->host copies inside the timed region (the socket streams 128-plane
+               rows: source bricks up, kernels, result rows down; h2d_bytes_per_step counts what was actually sent, summed
+               over the ranks)
   e2e_device_api  pipelined device API (pinned views -> H2D -> fused kernel -> D2H), for comparison
   roofline     fused kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json); algorithmic bytes =
                sum_v N_v*b_in + N*2 per launch
