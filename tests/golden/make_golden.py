@@ -7,7 +7,8 @@ h5pickle, skimage, ... are absent from the image and it targets numpy < 1.24.  T
 anyway, with
   * inert stand-ins (``MagicMock``) for modules the fusion path never calls (h5py, skimage, networkx, ...);
   * a minimal *eager* stand-in for ``dask.array`` (zeros/empty/from_array/map_blocks/rechunk/compute with
-    ``block_info``), enough to run ``affine_transform_dask`` and ``get_weights_dct_dask`` unchanged;
+    ``block_info`` and ``drop_axis``), enough to run ``affine_transform_dask``, ``get_weights_dct_dask`` and
+    ``illumination_fusion_planewise`` unchanged;
   * a SimpleITK stand-in whose ``Resample``/``Clamp`` are the oracle's ITK RESTATEMENT
     (``oracle.mvregfus_oracle.itk_resample``).  Outputs that pass through it (blending weights, PSF rotation,
     coarse-weight upsampling) therefore pin the reference's *Python* arithmetic around ITK but NOT ITK's own
