@@ -406,7 +406,7 @@ def _init_estimate(plan):
     groups whose partial estimates are added."""
     plan.sums.zero_()
     code, est = dtype_code(plan.views[0]), plan.est
-    cap = 8
+    cap = _cabi.MVF_MAX_VIEWS
     if plan.n <= cap:
         _cabi.check(plan.lib.mvf_rl_init_estimate(plan.n, plan._vp, code, plan._wp, C.c_void_p(est.data_ptr()), est.numel(),
                                                   C.c_void_p(plan.sums.data_ptr()), _stream_ptr()))
