@@ -190,3 +190,54 @@ def test_row_streamed_socket_equals_whole_upload(cuda, dtype, monkeypatch):
     ref = np.asarray(O.fuse_blockwise(tvo, params, sp, props, fusion_block_overlap=0))
     d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
     assert d.max() <= 3 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
+
+
+class _RecordingH5File:
+    """In-memory stand-in for h5py.File (h5py is absent from the image): datasets land in a dict keyed by file name."""
+    store = {}
+
+    def __init__(self, fn, mode="r"):
+        self.fn = fn
+        if mode == "w":
+            _RecordingH5File.store[fn] = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def create_dataset(self, name, data=None, **kwargs):
+        _RecordingH5File.store[self.fn][name] = np.array(data)
+        return _RecordingH5File.store[self.fn][name]
+
+    def __getitem__(self, name):
+        return _RecordingH5File.store[self.fn][name]
+
+
+def test_file_based_entry_points_with_recording_h5py(cuda, monkeypatch):
+    """transform_view_dask_and_save_chunked (mv:1746-1769) and the file-based fuse_blockwise (mv:3637-3813) hand HDF5 'Data'
+    sets from one to the other; with a recording stand-in for h5py both run end to end and match the oracle."""
+    import sys
+    import types
+    from mvregfus_b200 import multiview as mv
+    from tests.helpers import small_case
+    stub = types.ModuleType("h5py")
+    stub.File = _RecordingH5File
+    monkeypatch.setitem(sys.modules, "h5py", stub)
+    _RecordingH5File.store.clear()
+    views, params, props, sp = small_case(shape=(40, 36, 44), nviews=2, dtype=np.uint16, seed=5)
+    fns = [mv.transform_view_dask_and_save_chunked("tview_%d.h5" % i, views[i], params, i, sp) for i in range(2)]
+    assert fns == ["tview_0.h5", "tview_1.h5"]
+    tvo = [np.asarray(O.transform_stack_dask_numpy(v, p, sp)) for v, p in zip(views, params)]
+    for fn, ref in zip(fns, tvo):
+        got = _RecordingH5File.store[fn]["Data"]
+        d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+        assert got.dtype == ref.dtype and d.max() <= 1 and np.mean(d > 0) <= 2e-3
+    res = mv.fuse_blockwise("fused.h5", fns, params, sp, props, fusion_block_overlap=4,
+                            weights_func=mv.get_weights_simple, fusion_func=mv.fuse_views_weights)
+    stored = [_RecordingH5File.store[fn]["Data"] for fn in fns]
+    ref = np.asarray(O.fuse_blockwise(stored, params, sp, props, fusion_block_overlap=4))
+    d = np.abs(np.asarray(res).astype(np.int64) - ref.astype(np.int64))
+    assert d.max() <= 2 and np.mean(d > 0) <= 5e-3, (d.max(), np.mean(d > 0))
+    assert np.array_equal(_RecordingH5File.store["fused.h5"]["Data"], np.asarray(res))
