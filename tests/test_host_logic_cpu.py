@@ -78,3 +78,23 @@ def test_chunk_decisions_follow_fuse_block():
                           copy(2),   # only view 2 has weight: copy it
                           copy(1),   # no weighted view: first live view
                           copy(1)]   # views 0 and 1 live, view 0 dropped by the probe: copy view 1
+
+
+def test_dask_wrap_is_taken_when_dask_is_importable(monkeypatch):
+    """The resampling entry points return dask arrays when dask is installed (the reference's contract, mv:1458-1519); the
+    image has no dask, so the wrap is exercised with a stand-in module."""
+    import sys
+    import types
+    calls = []
+    da = types.ModuleType("dask.array")
+    da.from_array = lambda x, chunks=None: (calls.append((x.shape, chunks)), ("wrapped", x))[1]
+    dask = types.ModuleType("dask")
+    dask.array = da
+    monkeypatch.setitem(sys.modules, "dask", dask)
+    monkeypatch.setitem(sys.modules, "dask.array", da)
+    a = np.zeros((4, 6, 8), dtype=np.uint16)
+    out = mv._maybe_dask(a, (2, 3, 4))
+    assert out[0] == "wrapped" and out[1] is a and calls == [((4, 6, 8), (2, 3, 4))]
+    monkeypatch.delitem(sys.modules, "dask.array")
+    monkeypatch.setitem(sys.modules, "dask", None)      # import dask.array -> ImportError: plain ndarray back
+    assert mv._maybe_dask(a, (2, 3, 4)) is a
